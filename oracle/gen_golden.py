@@ -1,0 +1,338 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Container-only script (needs /root/reference).
+
+Runs the UNMODIFIED reference Python (oracle/ref_shims.py) on seeded inputs, checks that
+oracle/render_oracle.py reproduces it, and writes the golden fixtures under tests/golden/:
+
+  hash_cases.npz    hash/dense grid encoder: K1 forward + dy_dx, K2/K3 first backward,
+                    K4/K5 second backward, through the reference's own autograd wiring
+                    (hashencoder/hashgrid.py) on top of oracle/hashgrid_oracle.c
+  step_tracking.npz / step_mapping.npz
+                    SLAMNetwork.forward + SLAMLoss + backward (model/network.py, model/loss.py):
+                    inputs, weights, the random draws, every output tensor, the loss terms and the
+                    gradients w.r.t. all grids, all MLP parameters and the 7-vector camera poses
+  fine_mlp_pretrain.npz
+                    the real fine-level SDF MLP weights shipped as code/pretrain.pth
+                    (consumed by volsdf_train.py:139-147) — non-degenerate weights for parity tests
+
+Usage:  python -m oracle.gen_golden        (from the repo root; ~1 min on 8 cores)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_shims
+from . import render_oracle as ro
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def relerr(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+# ------------------------------------------------------------------------------- hash cases
+HASH_CASES = [
+    # name, L, C, base, end, logmap, B
+    ("dense_c8", 2, 8, 4, 8, 19, 193),
+    ("mixed_c4", 4, 4, 4, 24, 9, 257),      # levels 0-1 dense, 2-3 hashed
+    ("hashed_c2", 6, 2, 4, 64, 8, 300),
+    ("single_level_c2", 1, 2, 5, 5, 19, 64),
+]
+
+
+def gen_hash(ref):
+    out = {}
+    for name, L, C, base, end, logmap, B in HASH_CASES:
+        torch.manual_seed(100 + len(out))
+        enc = ref.hashgrid.HashEncoder(input_dim=3, num_levels=L, level_dim=C, per_level_scale=2,
+                                       base_resolution=base, log2_hashmap_size=logmap,
+                                       desired_resolution=end if L > 1 else None)
+        if L == 1:
+            enc.per_level_scale = 1.0
+        enc.embeddings.data.uniform_(-1, 1)
+        x = torch.rand(B, 3) * 2.2 - 1.1           # ~17% of points outside [-1,1] -> OOB path
+        x[0] = torch.tensor([-1.0, -1.0, -1.0])    # exact lower corner
+        x[1] = torch.tensor([1.0, 1.0, 1.0])       # exact upper corner (pos_grid+1 == resolution)
+        x[2] = torch.tensor([0.0, 1.0, -1.0])
+        x[3] = torch.tensor([1.0000001, 0.0, 0.0])
+        x.requires_grad_(True)
+        y = enc(x)
+        gy = torch.randn_like(y)
+        (gx,) = torch.autograd.grad(y, x, gy, create_graph=True)
+        ggx = torch.randn_like(gx)
+        # first-order grads of <y,gy> and second-order grads of <gx,ggx>
+        gtab1 = torch.autograd.grad(y, enc.embeddings, gy, retain_graph=True)[0]
+        # second order: d<gx,ggx>/d(gy) is not reachable through y; take it w.r.t. the upstream grad directly
+        gy2 = gy.clone().requires_grad_(True)
+        (gx2,) = torch.autograd.grad(enc(x), x, gy2, create_graph=True)
+        g_gy, gtab2 = torch.autograd.grad(gx2, [gy2, enc.embeddings], ggx)
+        # standalone oracle wiring must agree with the reference wiring bit for bit (same C library)
+        spec = ro.GridSpec(L, C, base, end, logmap)
+        assert np.array_equal(spec.offsets_np, enc.offsets.numpy()), name
+        xo = x.detach().clone().requires_grad_(True)
+        tab = enc.embeddings.detach().clone().requires_grad_(True)
+        yo = ro.hash_encode(xo, tab, spec.offsets, enc.per_level_scale, base)
+        assert torch.equal(yo, y), name
+        gy3 = gy.clone().requires_grad_(True)
+        (gxo,) = torch.autograd.grad(yo, xo, gy3, create_graph=True)
+        assert torch.equal(gxo, gx), name
+        g_gy_o, gtab2_o = torch.autograd.grad(gxo, [gy3, tab], ggx)
+        assert torch.equal(g_gy_o, g_gy) and torch.equal(gtab2_o, gtab2), name
+        for k, v in dict(x=x, table=enc.embeddings, offsets=enc.offsets, y=y, gy=gy, gx=gx, gtab1=gtab1, ggx=ggx,
+                         g_gy=g_gy, gtab2=gtab2).items():
+            out[f"{name}.{k}"] = _np(v)
+        out[f"{name}.meta"] = np.array([L, C, base, end, logmap, float(enc.per_level_scale)], dtype=np.float64)
+        print(f"[hash] {name}: B={B} entries={spec.n_entries} oob={(x.detach().abs() > 1).any(1).sum().item()}")
+    np.savez_compressed(os.path.join(OUT, "hash_cases.npz"), **out)
+
+
+# ------------------------------------------------------------------------------- full step
+TINY = dict(
+    H=24, W=32, feature=64,
+    coarse=dict(L=2, C=8, base=4, end=8, logmap=19, hidden=[64]),
+    fine=dict(L=4, C=4, base=4, end=16, logmap=10, hidden=[64, 64, 64]),
+    color=dict(L=16, C=2, base=4, end=48, logmap=9, hidden=[64, 64]),
+    sampler=dict(near=0.0, N_samples=12, N_samples_eval=40, N_samples_extra=6),
+)
+
+LOSS_W = dict(assign_scale_shift_init=True, warp_loss_weight=0.5, warp_loss_type="l1", rgb_loss="torch.nn.L1Loss",
+              eikonal_weight=0.1, smooth_weight=0.005, depth_weight=0.1, normal_l1_weight=0.05,
+              normal_cos_weight=0.05, flow_weight=0.001)
+TRACK_W = dict(rgb_loss="torch.nn.L1Loss", eikonal_weight=0, smooth_weight=0, depth_weight=0, normal_l1_weight=0,
+               normal_cos_weight=0)
+
+
+def tiny_model_conf(t=TINY):
+    def net(c, bias):
+        return dict(d_in=3, d_out=1, dims=c["hidden"], geometric_init=True, bias=bias, skip_in=[], weight_norm=True,
+                    multires=6, inside_outside=True, use_grid_feature=True, base_size=c["base"], end_size=c["end"],
+                    logmap=c["logmap"], num_levels=c["L"], level_dim=c["C"], divide_factor=1.0,
+                    embedding_method="nerf")
+    return ref_shims.to_conf(dict(
+        feature_vector_size=t["feature"], scene_bounding_sphere=1.0, use_warp_loss=True, mapping_patchsizes=[1],
+        tracking_patchsizes=[1], sampling_method="important", density_method="volsdf_gridpredefined",
+        implicit_network=dict(coarse=net(t["coarse"], 0.6), fine=net(t["fine"], 0.6)),
+        rendering_network=dict(mode="idr", d_in=9, d_out=3, dims=t["color"]["hidden"], weight_norm=True,
+                               multires_view=4, per_image_code=False, use_grid_feature=True),
+        gridpredefinedensity={}, ray_sampler=t["sampler"],
+    ))
+
+
+def build_reference_model(ref, t=TINY):
+    """Unmodified SLAMNetwork; only the hard-coded 2^24-entry color grid ctor args are swapped for tiny ones."""
+    HE = ref.hashgrid.HashEncoder
+    c = t["color"]
+
+    def small_color(**kw):
+        if kw.get("log2_hashmap_size") == 24:
+            kw.update(num_levels=c["L"], level_dim=c["C"], base_resolution=c["base"], desired_resolution=c["end"],
+                      log2_hashmap_size=c["logmap"])
+        return HE(**kw)
+
+    ref.base_networks.HashEncoder = small_color
+    try:
+        ds = type("DS", (), {"img_res": [t["H"], t["W"]], "data_dir": "synthetic"})()
+        model = ref.network.SLAMNetwork(tiny_model_conf(t), dataset=ds, n_images=4)
+    finally:
+        ref.base_networks.HashEncoder = HE
+    return model, ds
+
+
+def make_params(t=TINY, seed=10):
+    cs, fs, ks = (ro.GridSpec(t[k]["L"], t[k]["C"], t[k]["base"], t[k]["end"], t[k]["logmap"])
+                  for k in ("coarse", "fine", "color"))
+    params = {
+        "coarse": ro.make_sdf_net(cs, t["coarse"]["hidden"], t["feature"], seed=seed + 1, table_scale=0.3),
+        "fine": ro.make_sdf_net(fs, t["fine"]["hidden"], t["feature"], seed=seed + 2, table_scale=0.3),
+        "color": ro.make_color_net(ks, t["color"]["hidden"], t["feature"], seed=seed + 3, table_scale=0.3),
+    }
+    gen = torch.Generator().manual_seed(seed + 4)
+    params["voxels"] = torch.poisson(torch.full((64, 64, 64), 50.0), generator=gen)
+    # make the SDF change sign along rays so that the foreground mask / density are non-trivial:
+    # last-layer sdf row bias ~ small
+    return params
+
+
+def load_params_into_reference(model, params):
+    sd = {}
+    for ours, theirs in (("coarse", "implicit_network.coarse"), ("fine", "implicit_network.fine"),
+                         ("color", "rendering_network")):
+        p = params[ours]
+        sd[f"{theirs}.encoding.embeddings"] = p["table"].detach().clone()
+        for i, (v, g, b) in enumerate(p["layers"]):
+            sd[f"{theirs}.lin{i}.weight_v"] = v.detach().clone()
+            sd[f"{theirs}.lin{i}.weight_g"] = g.detach().clone()
+            sd[f"{theirs}.lin{i}.bias"] = b.detach().clone()
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(("offsets" in m) or ("embeddings" not in m and "lin" not in m) for m in missing), missing
+    model.voxels = params["voxels"].clone()
+    model.density.voxels = model.voxels
+
+
+def synth_batch(t, bs, npix, seed):
+    gen = torch.Generator().manual_seed(seed)
+    H, W = t["H"], t["W"]
+    K = torch.eye(4)[None].repeat(bs, 1, 1)
+    K[:, 0, 0] = K[:, 1, 1] = 0.9 * W
+    K[:, 0, 2], K[:, 1, 2] = (W - 1) / 2, (H - 1) / 2
+    # cameras inside the unit cube looking roughly along +z with small perturbations
+    quat = torch.tensor([1.0, 0.0, 0.0, 0.0])[None].repeat(bs, 1) + 0.08 * torch.randn(bs, 4, generator=gen)
+    trans = 0.25 * torch.randn(bs, 3, generator=gen) + torch.tensor([0.0, 0.0, -0.4])
+    cam7 = torch.cat([quat, trans], 1)
+    sidx = torch.randint(H * W, (npix,), generator=gen)
+    uvfull = torch.stack(torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy"), -1).reshape(-1, 2).float()
+    uv = uvfull[sidx][None].repeat(bs, 1, 1)
+    full_rgb = torch.rand(bs, H * W, 3, generator=gen)
+    gt = {
+        "full_rgb": full_rgb, "rgb": full_rgb[:, sidx], "mask": torch.ones(bs, npix, 1),
+        "depth": torch.rand(bs, npix, 1, generator=gen),
+        "normal": torch.nn.functional.normalize(torch.randn(bs, npix, 3, generator=gen), dim=-1),
+        "full_depth": torch.rand(bs, H * W, 1, generator=gen) * 1.5 + 0.5,
+    }
+    gt["gt_depth"] = gt["full_depth"][:, sidx]
+    return K, cam7, uv, sidx, gt
+
+
+def gen_step(ref, mode, fname, bs, npix, frame_idx, stage, color_stage, seed):
+    t = TINY
+    params = make_params(t)
+    model, ds = build_reference_model(ref, t)
+    load_params_into_reference(model, params)
+    model.train()
+    K, cam7, uv, sidx, gt = synth_batch(t, bs, npix, seed)
+    if mode == "mapping":
+        ii = torch.tensor([0, 1]); jj = torch.tensor([1, 0])
+        gt["edges"] = (ii, jj, ii * 10, jj * 10)
+        gen = torch.Generator().manual_seed(seed + 99)
+        gt["flow"] = torch.randn(2, npix, 2, generator=gen) * 3
+        gt["flow_mask"] = torch.rand(2, npix, generator=gen) > 0.3
+    w = LOSS_W if mode == "mapping" else TRACK_W
+    loss_mod = ref.loss.SLAMLoss(trainer=None, train_dataset=ds, scan_id=2, model=model, **w)
+
+    # ---- reference
+    cam_ref = cam7.clone().requires_grad_(True)
+    torch.manual_seed(seed)
+    inp = {"intrinsics": K, "uv": uv, "pose": ref.general.get_camera_from_tensor(cam_ref), "sampling_idx": sidx}
+    out_ref = model(inp, torch.arange(bs), gt, keyframe_list=list(range(bs)), frame_idx=frame_idx, mode=mode,
+                    stage=stage, color_stage=color_stage)
+    lo_ref = loss_mod(out_ref, gt, list(range(bs)), frame_idx=frame_idx, stage=stage)
+    lo_ref["loss"].backward()
+    named = dict(model.named_parameters())
+
+    # ---- oracle, same seed -> same draws
+    leaves = ro.leaf_params(params)
+    cam_o = cam7.clone().requires_grad_(True)
+    cfg = dict(t["sampler"], scene_bounding_sphere=1.0, H=t["H"], W=t["W"], use_warp_loss=True,
+               mapping_patchsizes=[1], tracking_patchsizes=[1])
+    torch.manual_seed(seed)
+    rng = ro.TorchRng()
+    out_o = ro.render_forward({"intrinsics": K, "uv": uv, "pose": ro.camera_from_tensor(cam_o)}, gt, params, cfg,
+                              mode, stage, color_stage, training=True, rng=rng)
+    lo_o = ro.slam_loss(out_o, gt, w, frame_idx=frame_idx, stage=stage)
+    lo_o["loss"].backward()
+
+    def compare(out_o, lo_o, leaves, cam_o, tag, tol):
+        worst = 0.0
+        for k in ("rgb_values", "depth_values", "normal_map", "z_vals", "sdf", "weights", "rgb", "grad_theta",
+                  "grad_theta_nei", "flow"):
+            if k in out_ref:
+                e = relerr(out_o[k], out_ref[k]); worst = max(worst, e)
+                print(f"  [{mode}/{tag}] out {k:14s} rel {e:.2e}")
+        e = abs(float(lo_o["loss"]) - float(lo_ref["loss"])) / abs(float(lo_ref["loss"]))
+        print(f"  [{mode}/{tag}] loss ref={float(lo_ref['loss']):.8f} oracle={float(lo_o['loss']):.8f} rel {e:.2e}")
+        worst = max(worst, e)
+        grads = {}
+        for name, leaf in leaves.items():
+            net, rest = name.split(".", 1)
+            rname = mapping[net] + "." + ("encoding.embeddings" if rest == "table" else rest)
+            gr, go = named[rname].grad, leaf.grad
+            if gr is None:
+                assert go is None or float(go.abs().max()) == 0.0, name
+                continue
+            e = relerr(go, gr); worst = max(worst, e)
+            print(f"  [{mode}/{tag}] grad {name:28s} |g|={float(gr.norm()):.3e} rel {e:.2e}")
+            grads[name] = gr
+        e = relerr(cam_o.grad, cam_ref.grad); worst = max(worst, e)
+        print(f"  [{mode}/{tag}] grad cam7 |g|={float(cam_ref.grad.norm()):.3e} rel {e:.2e}")
+        assert worst < tol, f"oracle disagrees with the reference ({tag}): {worst}"
+        return worst, grads
+
+    mapping = {"coarse": "implicit_network.coarse", "fine": "implicit_network.fine", "color": "rendering_network"}
+    # (1) free-running sampler: 1-ulp weight differences are amplified by 1/beta and the CDF inversion
+    #      -> loose tolerance, this is the reference's own reorder-noise floor
+    worst_free, _ = compare(out_o, lo_o, leaves, cam_o, "free", 5e-3)
+    assert relerr(params["voxels"], model.voxels) == 0.0, "voxel counter mismatch"
+
+    # (2) frozen z (the reference's own samples): everything downstream must agree tightly
+    params2 = make_params(t)
+    leaves2 = ro.leaf_params(params2)
+    cam_o2 = cam7.clone().requires_grad_(True)
+    z_ref = out_ref["z_vals"].detach()
+    z_eik_ref = torch.gather(z_ref, 1, rng.rec["eik_index"].unsqueeze(-1))
+    out_o2 = ro.render_forward({"intrinsics": K, "uv": uv, "pose": ro.camera_from_tensor(cam_o2)}, gt, params2, cfg,
+                               mode, stage, color_stage, training=True, rng=ro.ReplayRng(rng.rec),
+                               z_override=(z_ref, z_eik_ref))
+    lo_o2 = ro.slam_loss(out_o2, gt, w, frame_idx=frame_idx, stage=stage)
+    lo_o2["loss"].backward()
+    worst, grads = compare(out_o2, lo_o2, leaves2, cam_o2, "frozen-z", 5e-5)
+
+    blob = {"K": K, "cam7": cam7, "uv": uv, "sidx": sidx}
+    blob.update({f"gt.{k}": v for k, v in gt.items() if torch.is_tensor(v)})
+    if "edges" in gt:
+        blob["gt.edges"] = torch.stack(gt["edges"])
+    blob.update({f"rng.{k}": v for k, v in rng.rec.items()})
+    blob["voxels_before"] = make_params(t)["voxels"]
+    blob["voxels_after"] = model.voxels
+    for k in ("rgb_values", "depth_values", "normal_map", "z_vals", "sdf", "weights", "rgb", "entropy", "depth_vals",
+              "grad_theta", "grad_theta_nei", "flow"):
+        if k in out_ref:
+            blob[f"out.{k}"] = out_ref[k]
+    if "warp_output" in out_ref:
+        g_, s_, m_, _ = out_ref["warp_output"][1]
+        blob["out.warp_gt"], blob["out.warp_sampled"], blob["out.warp_mask"] = g_, s_, m_
+    for k, v in lo_ref.items():
+        blob[f"loss.{k}"] = torch.as_tensor(v).float()
+    blob.update({f"grad.{k}": v for k, v in grads.items()})
+    blob["grad.cam7"] = cam_ref.grad
+    blob["meta"] = torch.tensor([bs, npix, frame_idx, seed])
+    np.savez_compressed(os.path.join(OUT, fname), **{k: _np(v) for k, v in blob.items()},
+                        stage=np.array(stage), color_stage=np.array(color_stage), mode=np.array(mode))
+    print(f"[step] wrote {fname}  worst oracle-vs-reference rel err: frozen-z {worst:.2e}, free sampler {worst_free:.2e}")
+
+
+def gen_pretrain():
+    sd = torch.load(os.path.join(ref_shims.REF_CODE, "pretrain.pth"), map_location="cpu", weights_only=False)
+    sd = sd["model_state_dict"]
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("implicit_network.fine.lin") or k.startswith("implicit_network.coarse.lin"):
+            out[k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "sdf_mlp_pretrain.npz"), **out)
+    print("[pretrain] wrote sdf_mlp_pretrain.npz:", {k: v.shape for k, v in out.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    ref = ref_shims.import_reference()
+    gen_hash(ref)
+    gen_step(ref, "tracking", "step_tracking.npz", bs=1, npix=96, frame_idx=3, stage="fine", color_stage="highfreq",
+             seed=21)
+    gen_step(ref, "mapping", "step_mapping.npz", bs=2, npix=64, frame_idx=5, stage="fine", color_stage="highfreq",
+             seed=22)
+    gen_step(ref, "mapping", "step_mapping_coarse_base.npz", bs=2, npix=48, frame_idx=5, stage="coarse",
+             color_stage="base", seed=23)
+    gen_pretrain()
+
+
+if __name__ == "__main__":
+    sys.exit(main())
