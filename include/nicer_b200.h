@@ -1,0 +1,173 @@
+/*
+ * nicer_b200.h — C ABI of libnicer_b200.so (hand-written sm_100a CUDA for the NICER-SLAM
+ * volume-rendering hot path).  Plain pointers and sizes only: every pointer is a DEVICE pointer
+ * unless named host_*, `stream` is a cudaStream_t passed as void*, and no function allocates:
+ * the caller owns every buffer (same ownership rule as the reference's native op).
+ *
+ * Every function returns 0 on success and a negative code on error; nicer_last_error() returns
+ * a thread-local message.  Launches are asynchronous on `stream`.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/code):
+ *   nicer_hash_encode_forward          <- hash_encode_forward          hashencoder/src/hashencoder.h:13, hashencoder.cu:758-781
+ *   nicer_hash_encode_backward         <- hash_encode_backward         hashencoder.h:14,  hashencoder.cu:783-813
+ *   nicer_hash_encode_second_backward  <- hash_encode_second_backward  hashencoder.h:15,  hashencoder.cu:816-854
+ *   nicer_sdf_forward / _backward      <- ImplicitNetworkGrid.forward/get_outputs/gradient + autograd double backward
+ *                                         model/base_networks.py:155-221 (hash encode + NeRF PE + weight-normed
+ *                                         Softplus(100) MLP + d sdf/dx computed in-kernel)
+ *   nicer_color_forward / _backward    <- RenderingNetwork.forward (mode "idr")  model/base_networks.py:333-392
+ *   nicer_outer_accum                  <- the nn.Linear weight/bias gradient GEMMs autograd runs for the above
+ *   nicer_composite_forward/_backward  <- GridPredefineDensity (model/density.py:33-67) + SLAMNetwork.volume_rendering
+ *                                         and the weighted sums (model/network.py:137-151,338-345,349-370)
+ *   nicer_voxel_count                  <- SLAMNetwork.update_voxels  model/network.py:62-76
+ */
+#ifndef NICER_B200_H
+#define NICER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NICER_MAX_LEVELS 16
+#define NICER_HIDDEN 64          /* hidden width of all three MLPs in every shipped conf */
+#define NICER_MAX_HIDDEN_LAYERS 4
+
+const char *nicer_last_error(void);
+int nicer_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Drop-in native op of hashencoder/ (same argument meaning and layouts as hashencoder.h:13-15).
+ *   inputs  [B,D] fp32 in [0,1] (points outside produce zeros / are skipped)
+ *   embeddings [N,C] fp32; offsets [L+1] int32 (device)
+ *   outputs / grad / grad_grad [L,B,C];  dy_dx [B,L,D,C]
+ *   accumulators (grad_embeddings, grad_inputs, grad2_embeddings) must arrive zeroed.
+ *   D in {2,3}; C in {1,2,4,8} (second_backward: C in {2,4,8}, as the reference).
+ * ------------------------------------------------------------------------------------------- */
+int nicer_hash_encode_forward(const float *inputs, const float *embeddings, const int32_t *offsets,
+                              float *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                              uint32_t H, int calc_grad_inputs, float *dy_dx, void *stream);
+
+int nicer_hash_encode_backward(const float *grad, const float *inputs, const float *embeddings,
+                               const int32_t *offsets, float *grad_embeddings, uint32_t B, uint32_t D,
+                               uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs,
+                               const float *dy_dx, float *grad_inputs, void *stream);
+
+int nicer_hash_encode_second_backward(const float *grad, const float *inputs, const float *embeddings,
+                                      const int32_t *offsets, uint32_t B, uint32_t D, uint32_t C,
+                                      uint32_t L, float S, uint32_t H, int calc_grad_inputs,
+                                      const float *dy_dx, const float *grad_grad_inputs, float *grad_grad,
+                                      float *grad2_embeddings, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused networks.  Conventions:
+ *   P            number of points (ray-samples)
+ *   x            [P,3] row-major world points in [-1,1]^3
+ *   "fm" buffers feature-major: [rows][P] (row stride P), so a warp of consecutive points is coalesced
+ *   weights      effective (weight-normed) matrices, row-major [out,in], fp32
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float *table;        /* [n_entries, C] */
+    const int32_t *offsets;    /* device [L+1] */
+    uint32_t L, C, H;          /* levels, features per level (2|4|8), base resolution */
+    float S;                   /* log2(per_level_scale) (hashgrid.py:31) */
+    float divide_factor;       /* ImplicitNetworkGrid.divide_factor (base_networks.py:158) */
+} nicer_grid_t;
+
+typedef struct {
+    nicer_grid_t grid;
+    uint32_t multires;         /* NeRF PE frequencies for x (6 in all confs) */
+    uint32_t n_hidden;         /* hidden layers of width 64: coarse 1, fine 3 */
+    uint32_t d_out;            /* 1 + feature_vector_size (65) */
+    const float *W[NICER_MAX_HIDDEN_LAYERS + 1];   /* W[0] [64,d_in], W[1..n-1] [64,64], W[n] [d_out,64] */
+    const float *b[NICER_MAX_HIDDEN_LAYERS + 1];
+} nicer_sdf_net_t;
+
+/* Workspace saved by nicer_sdf_forward for nicer_sdf_backward (all fm):
+ *   Z    [n_hidden*64][P]   pre-activations z_l
+ *   R    [(n_hidden-1)*64][P] adjoints r_l = d sdf / d a_l for l<n (r_n is W[n][0,:])   (may be NULL if n_hidden==1)
+ *   DYDX [L*3*C][P]         d enc / d u   (K1's dy_dx, feature-major)
+ */
+#define NICER_SDF_ONLY 1u        /* sdf only: no feat, no gradient, nothing saved (sampler pass, get_sdf_vals) */
+#define NICER_SDF_ACCUMULATE 2u  /* add into sdf/feat/grad instead of overwriting (coarse+fine sum, base_networks.py:40) */
+#define NICER_SDF_NO_FEAT 4u     /* gradient() path: sdf + gradient only (base_networks.py:195-206) */
+
+int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags,
+                      float *sdf /*[P]*/, float *feat_fm /*[64][P]*/, float *grad /*[P,3]*/,
+                      float *Z, float *R, float *DYDX, void *stream);
+
+/* Backward of (sdf, feat, grad) w.r.t. x, the grid and (through the workspace below) the weights.
+ *   g_sdf [P] | NULL, g_feat_fm [64][P] | NULL, g_grad [P,3] | NULL   upstream gradients
+ *   grad_x [P,3] | NULL       accumulated (+=)
+ *   grad_table [n_entries,C]  accumulated with atomics (first- and second-order terms both land here)
+ *   Outputs for nicer_outer_accum (all fm, written):
+ *     ZB  [n_hidden*64][P]  dL/dz_l          QB  [n_hidden*64][P]  q_l = r_l * softplus'(z_l)
+ *     AB  [n_hidden*64][P]  a_l              TAN [n_hidden*64][P]  tangent of a_l in direction g_grad
+ *     H0  [d_in][P]         network input    T0  [d_in][P]         tangent of the network input
+ */
+int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P,
+                       const float *Z, const float *R, const float *DYDX,
+                       const float *g_sdf, const float *g_feat_fm, const float *g_grad,
+                       float *grad_x, float *grad_table,
+                       float *ZB, float *QB, float *AB, float *TAN, float *H0, float *T0, void *stream);
+
+typedef struct {
+    nicer_grid_t grid;         /* grid.table == NULL: no color grid (use_grid_feature=false) */
+    uint32_t multires_view;    /* 4 */
+    uint32_t feature;          /* 64 */
+    uint32_t n_hidden;         /* 2 */
+    uint32_t grid_detached;    /* color_stage == "base" (base_networks.py:337-339): no grid / x gradient through it */
+    const float *W[NICER_MAX_HIDDEN_LAYERS + 1];   /* W[0] [64,d_in], ..., W[n] [3,64] */
+    const float *b[NICER_MAX_HIDDEN_LAYERS + 1];
+} nicer_color_net_t;
+
+/* rgb [P,3] = sigmoid(MLP([x, PE(view), normals, feat, grid(x)])).  A_fm [n_hidden*64][P] saved (post-ReLU).
+ * DYDX [L*3*C][P] saved only when want_dx (x requires grad and grid not detached), else NULL. */
+int nicer_color_forward(const nicer_color_net_t *net, const float *x, const float *view /*[P,3]*/,
+                        const float *normals /*[P,3]*/, const float *feat_fm /*[64][P]*/, uint32_t P,
+                        float *rgb, float *A_fm, float *DYDX, void *stream);
+
+/* g_rgb [P,3] upstream.  Outputs: grad_x (+=, NULL ok), grad_view [P,3] (written, NULL ok),
+ * grad_normals [P,3] (written), grad_feat_fm [64][P] (written), grad_table (atomics, NULL when detached),
+ * ZB [n_hidden*64][P] dL/dz_l, OB [3][P] dL/d(pre-sigmoid), H0 [d_in][P] network input (for nicer_outer_accum). */
+int nicer_color_backward(const nicer_color_net_t *net, const float *x, const float *view,
+                         const float *normals, const float *feat_fm, uint32_t P, const float *rgb,
+                         const float *A_fm, const float *DYDX, const float *g_rgb,
+                         float *grad_x, float *grad_view, float *grad_normals, float *grad_feat_fm,
+                         float *grad_table, float *ZB, float *OB, float *H0, void *stream);
+
+/* C[M,N] (row stride ldc) += A[M][P] * B[N][P]^T ;  bias[M] += rowsum(A) when bias != NULL.
+ * A, B feature-major with row strides lda, ldb (>= P).  M <= 64, N <= 144. */
+int nicer_outer_accum(const float *A, uint32_t lda, uint32_t M, const float *B, uint32_t ldb, uint32_t N,
+                      uint32_t P, float *C, uint32_t ldc, float *bias, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Density + alpha compositing, one warp per ray.  R rays x S samples (S <= 1024), P = R*S.
+ *   sdf [P], x [P,3] (for the beta lookup), z [R,S], rgb [P,3], grad [P,3] (SDF gradients), voxels [res^3]
+ *   outputs: weights [R,S], rgb_out [R,3], depth_out [R] (= sum w z / (sum w + 1e-8)), normal_out [R,3]
+ *            (= sum w g/(|g|+1e-6), before the R^T rotation), wsum [R]
+ * ------------------------------------------------------------------------------------------- */
+int nicer_composite_forward(const float *sdf, const float *x, const float *z, const float *rgb,
+                            const float *grad, const float *voxels, uint32_t voxel_res, uint32_t R,
+                            uint32_t S, float *weights, float *rgb_out, float *depth_out,
+                            float *normal_out, float *wsum, void *stream);
+
+/* upstream: g_rgb_out [R,3] | NULL, g_depth_out [R] | NULL, g_normal_out [R,3] | NULL, g_weights [R,S] | NULL.
+ * outputs (written): g_sdf [P], g_rgb [P,3], g_grad [P,3]. */
+int nicer_composite_backward(const float *sdf, const float *x, const float *z, const float *rgb,
+                             const float *grad, const float *voxels, uint32_t voxel_res, uint32_t R,
+                             uint32_t S, const float *weights, const float *depth_out, const float *wsum,
+                             const float *g_rgb_out, const float *g_depth_out, const float *g_normal_out,
+                             const float *g_weights, float *g_sdf, float *g_rgb, float *g_grad, void *stream);
+
+/* Sampler weights: density + transmittance for the no-grad pass (ray_sampler.py:105-112). weights [R,S]. */
+int nicer_sampler_weights(const float *sdf, const float *x, const float *z, const float *voxels,
+                          uint32_t voxel_res, uint32_t R, uint32_t S, float *weights, void *stream);
+
+/* voxels[idx(x)] += 1 for every point with all |x_i| <= 0.99 (network.py:62-76). */
+int nicer_voxel_count(const float *x, uint32_t P, float *voxels, uint32_t voxel_res, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NICER_B200_H */

@@ -1,0 +1,104 @@
+"""ctypes binding of libnicer_b200.so (include/nicer_b200.h).
+
+There is no CPU fallback: if the library is missing or a tensor is not a contiguous fp32 CUDA tensor the
+call raises.  Build with ``python -m nicer_slam_b200.build`` (nvcc, sm_100a).
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnicer_b200.so")
+
+MAX_LAYERS = 5  # NICER_MAX_HIDDEN_LAYERS + 1
+
+_fp = C.c_void_p
+_u32 = C.c_uint32
+
+
+class GridT(C.Structure):
+    _fields_ = [("table", _fp), ("offsets", _fp), ("L", _u32), ("C", _u32), ("H", _u32), ("S", C.c_float),
+                ("divide_factor", C.c_float)]
+
+
+class SdfNetT(C.Structure):
+    _fields_ = [("grid", GridT), ("multires", _u32), ("n_hidden", _u32), ("d_out", _u32),
+                ("W", _fp * MAX_LAYERS), ("b", _fp * MAX_LAYERS)]
+
+
+class ColorNetT(C.Structure):
+    _fields_ = [("grid", GridT), ("multires_view", _u32), ("feature", _u32), ("n_hidden", _u32),
+                ("grid_detached", _u32), ("W", _fp * MAX_LAYERS), ("b", _fp * MAX_LAYERS)]
+
+
+_SIGS = {
+    "nicer_hash_encode_forward": [_fp, _fp, _fp, _fp, _u32, _u32, _u32, _u32, C.c_float, _u32, C.c_int, _fp, _fp],
+    "nicer_hash_encode_backward": [_fp, _fp, _fp, _fp, _fp, _u32, _u32, _u32, _u32, C.c_float, _u32, C.c_int, _fp,
+                                   _fp, _fp],
+    "nicer_hash_encode_second_backward": [_fp, _fp, _fp, _fp, _u32, _u32, _u32, _u32, C.c_float, _u32, C.c_int, _fp,
+                                          _fp, _fp, _fp, _fp],
+    "nicer_sdf_forward": [C.POINTER(SdfNetT), _fp, _u32, _u32, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
+    "nicer_sdf_backward": [C.POINTER(SdfNetT), _fp, _u32] + [_fp] * 15,
+    "nicer_color_forward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32, _fp, _fp, _fp, _fp],
+    "nicer_color_backward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32] + [_fp] * 13,
+    "nicer_outer_accum": [_fp, _u32, _u32, _fp, _u32, _u32, _u32, _fp, _u32, _fp, _fp],
+    "nicer_composite_forward": [_fp] * 6 + [_u32, _u32, _u32] + [_fp] * 6,
+    "nicer_composite_backward": [_fp] * 6 + [_u32, _u32, _u32] + [_fp] * 11,
+    "nicer_sampler_weights": [_fp] * 4 + [_u32, _u32, _u32, _fp, _fp],
+    "nicer_voxel_count": [_fp, _u32, _fp, _u32, _fp],
+}
+
+_handle = None
+
+
+def _bind(h):
+    for name, sig in _SIGS.items():
+        fn = getattr(h, name)  # AttributeError if the library lacks a declared symbol
+        fn.argtypes = sig
+        fn.restype = C.c_int
+    h.nicer_last_error.restype = C.c_char_p
+    h.nicer_version.restype = C.c_int
+    return h
+
+
+def lib():
+    global _handle
+    if _handle is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is not built (python -m nicer_slam_b200.build). "
+                "nicer_slam_b200 has no CPU fallback.")
+        _handle = _bind(C.CDLL(LIB_PATH))
+    return _handle
+
+
+def exported_symbols():
+    return sorted(list(_SIGS) + ["nicer_last_error", "nicer_version"])
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().nicer_last_error()
+        raise RuntimeError(f"libnicer_b200 {what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def require(t, dtype=torch.float32, name="tensor"):
+    """Device/contiguity/dtype guard (the reference's CHECK_CUDA / CHECK_CONTIGUOUS, hashencoder.cu:16-19)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def ptr(t, dtype=torch.float32, name="tensor"):
+    if t is None:
+        return None
+    return C.c_void_p(require(t, dtype, name).data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

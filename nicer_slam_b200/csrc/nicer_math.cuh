@@ -1,0 +1,231 @@
+// Per-point math shared by every kernel (and compiled for the host by tests/host_emul to check the
+// formulas on a CPU-only box).  No reference code: the algorithms follow
+// /root/reference/code/hashencoder/src/hashencoder.cu (index/hash :35-73, smoothstep :115-121,
+// K1 :131-283, K2 :286-373, K5 :461-625) and torch's softplus / weight-normed Linear semantics
+// (model/base_networks.py:149-179), restated for a one-thread-per-point formulation.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define NHD __host__ __device__ __forceinline__
+#define NDEV __device__ __forceinline__
+#else
+#define NHD inline
+#define NDEV inline
+#include <string.h>
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { float4 v = {a, b, c, d}; return v; }
+static inline float2 make_float2(float a, float b) { float2 v = {a, b}; return v; }
+#endif
+
+#define NICER_W 64  // hidden width
+
+namespace nicer {
+
+// ------------------------------------------------------------------ activations
+// torch.nn.Softplus(beta=100, threshold=20) and its first / second derivative
+// (ATen softplus, softplus_backward, softplus_double_backward).
+constexpr float SP_BETA = 100.0f;
+constexpr float SP_THRESH = 20.0f;
+
+NHD float softplus100(float z) {
+    float t = z * SP_BETA;
+    return t > SP_THRESH ? z : log1pf(expf(t)) / SP_BETA;
+}
+NHD float dsoftplus100(float z) {
+    float t = z * SP_BETA;
+    if (t > SP_THRESH) return 1.0f;
+    float e = expf(t);
+    return e / (e + 1.0f);
+}
+NHD float d2softplus100(float z) {
+    float t = z * SP_BETA;
+    if (!(t < SP_THRESH)) return 0.0f;
+    float s = 1.0f / (1.0f + expf(-t));
+    return (1.0f - s) * s * SP_BETA;
+}
+
+NHD float sstep(float v) { return v * v * (3.0f - 2.0f * v); }
+NHD float sstep_d(float v) { return 6.0f * v * (1.0f - v); }
+
+// ------------------------------------------------------------------ grid geometry
+struct LevelInfo {
+    uint32_t offset;        // first entry of the level
+    uint32_t hashmap_size;  // entries in the level
+    uint32_t resolution;    // ceil(scale) + 1
+    float scale;            // exp2f(level*S)*H - 1
+};
+
+NHD LevelInfo make_level(const int32_t *offsets, uint32_t level, float S, uint32_t H) {
+    LevelInfo li;
+    li.offset = (uint32_t)offsets[level];
+    li.hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
+    li.scale = exp2f((float)level * S) * (float)H - 1.0f;
+    li.resolution = (uint32_t)ceilf(li.scale) + 1u;
+    return li;
+}
+
+// entry index (not multiplied by C) of grid vertex p within a level
+NHD uint32_t vertex_index3(const LevelInfo &li, uint32_t px, uint32_t py, uint32_t pz) {
+    uint32_t stride = 1, index = 0;
+    const uint32_t hs = li.hashmap_size, res = li.resolution;
+    if (stride <= hs) { index += px * stride; stride *= res; }
+    if (stride <= hs) { index += py * stride; stride *= res; }
+    if (stride <= hs) { index += pz * stride; stride *= res; }
+    if (stride > hs) index = (px * 1u) ^ (py * 2654435761u) ^ (pz * 805459861u);
+    return index % hs;
+}
+
+// Interpolation cell of a point u in [0,1]^3 at one level.
+struct Cell3 {
+    uint32_t pg[3];
+    float w[3];   // smoothstep(frac)
+    float dw[3];  // smoothstep'(frac)
+    float scale;
+    bool inside;
+};
+
+NHD Cell3 locate3(const LevelInfo &li, const float u[3]) {
+    Cell3 c;
+    c.inside = !(u[0] < 0.f || u[0] > 1.f || u[1] < 0.f || u[1] > 1.f || u[2] < 0.f || u[2] > 1.f);
+    c.scale = li.scale;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float p = u[d] * li.scale;
+        float f = floorf(p);
+        c.pg[d] = (uint32_t)f;
+        p -= (float)c.pg[d];
+        c.dw[d] = sstep_d(p);
+        c.w[d] = sstep(p);
+    }
+    return c;
+}
+
+NHD void corner_indices(const LevelInfo &li, const Cell3 &c, uint32_t idx[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        idx[k] = vertex_index3(li, c.pg[0] + (k & 1), c.pg[1] + ((k >> 1) & 1), c.pg[2] + ((k >> 2) & 1));
+}
+
+// trilinear weights in the reference's corner order (bit d of k selects the upper vertex in dim d)
+NHD void corner_weights(const Cell3 &c, float wt[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float w = 1.0f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) w *= ((k >> d) & 1) ? c.w[d] : 1.0f - c.w[d];
+        wt[k] = w;
+    }
+}
+
+// d(feature)/d(u_gd) weights per corner: scale * s'(f_gd) * prod_{d != gd} w_d, signed (+ upper, - lower)
+NHD void corner_dweights(const Cell3 &c, int gd, float wt[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float w = c.scale;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            if (d != gd) w *= ((k >> d) & 1) ? c.w[d] : 1.0f - c.w[d];
+        w *= c.dw[gd];
+        wt[k] = ((k >> gd) & 1) ? w : -w;
+    }
+}
+
+template <int C>
+NHD void load_entry(const float *table, const LevelInfo &li, uint32_t idx, float out[C]) {
+    const float *p = table + ((size_t)li.offset + idx) * C;
+    if constexpr (C == 8) {
+        float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+        out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+        out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+    } else if constexpr (C == 4) {
+        float4 a = *reinterpret_cast<const float4 *>(p);
+        out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    } else if constexpr (C == 2) {
+        float2 a = *reinterpret_cast<const float2 *>(p);
+        out[0] = a.x; out[1] = a.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c] = p[c];
+    }
+}
+
+// Level encode of a point: features feat[C] and (optionally) d feat / d u  dfeat[3][C].
+// Out-of-range points give zeros (hashencoder.cu:152-177).
+template <int C, bool WITH_DX>
+NHD void encode_level(const float *table, const LevelInfo &li, const float u[3], float feat[C], float dfeat[3][C]) {
+    Cell3 c = locate3(li, u);
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        feat[ch] = 0.f;
+        if (WITH_DX) { dfeat[0][ch] = 0.f; dfeat[1][ch] = 0.f; dfeat[2][ch] = 0.f; }
+    }
+    if (!c.inside) return;
+    uint32_t idx[8];
+    corner_indices(li, c, idx);
+    float val[8][C];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) load_entry<C>(table, li, idx[k], val[k]);
+    float wt[8];
+    corner_weights(c, wt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) feat[ch] += wt[k] * val[k][ch];
+    if (WITH_DX) {
+#pragma unroll
+        for (int gd = 0; gd < 3; ++gd) {
+            // the reference sums (right-left) pairs: w * (v_r - v_l) * s'(f)  (hashencoder.cu:245-276)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if ((k >> gd) & 1) continue;
+                float w = c.scale;
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    if (d != gd) w *= ((k >> d) & 1) ? c.w[d] : 1.0f - c.w[d];
+                const int kr = k | (1 << gd);
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) dfeat[gd][ch] += w * (val[kr][ch] - val[k][ch]) * c.dw[gd];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ small dense helpers
+// acc[0..63] += a * row[0..63]   (row 16-byte aligned)
+NHD void axpy64(float acc[NICER_W], const float *row, float a) {
+    const float4 *w = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+    for (int j = 0; j < NICER_W / 4; ++j) {
+        float4 v = w[j];
+        acc[4 * j + 0] += v.x * a;
+        acc[4 * j + 1] += v.y * a;
+        acc[4 * j + 2] += v.z * a;
+        acc[4 * j + 3] += v.w * a;
+    }
+}
+
+// sum_j row[j] * q[j]
+NHD float dot64(const float *row, const float q[NICER_W]) {
+    const float4 *w = reinterpret_cast<const float4 *>(row);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NICER_W / 4; ++j) {
+        float4 v = w[j];
+        s0 += v.x * q[4 * j + 0];
+        s1 += v.y * q[4 * j + 1];
+        s2 += v.z * q[4 * j + 2];
+        s3 += v.w * q[4 * j + 3];
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+// acc += Wt[K][64]^T-applied: acc[j] += sum_k Wt[k][j] * col[k*cs]
+NHD void mv_acc64(float acc[NICER_W], const float *Wt, const float *col, int cs, int K) {
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) axpy64(acc, Wt + k * NICER_W, col[k * cs]);
+}
+
+}  // namespace nicer

@@ -1,0 +1,386 @@
+"""Autograd bindings of the fused CUDA kernels (libnicer_b200.so).
+
+Every Function here is once-differentiable *by construction*: the SDF network returns its own analytic
+gradient d sdf/dx as a regular output and its backward contains the second-order terms, so no
+``create_graph`` double backward is needed (the reference: model/base_networks.py:195-221 +
+hashencoder/hashgrid.py:54-134).
+
+Layouts: points are [P,3] row-major; wide per-point tensors are kept feature-major ([rows, P]) inside the
+library and exposed to PyTorch as transposed *views* ([P, rows]) so no copy is made between kernels.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ColorNetT, GridT, SdfNetT
+
+
+def lib():
+    return _lib.lib()
+
+
+def check(rc, what=""):
+    return _lib.check(rc, what)
+
+
+def ptr(t, dtype=torch.float32, name="tensor"):
+    return _lib.ptr(t, dtype, name)
+
+
+def stream():
+    return _lib.stream()
+
+
+HIDDEN = 64
+F_SDF_ONLY, F_ACCUMULATE, F_NO_FEAT = 1, 2, 4
+
+
+@dataclass(frozen=True)
+class GridMeta:
+    L: int
+    C: int
+    H: int
+    S: float            # log2(per_level_scale)
+    divide_factor: float = 1.0
+
+
+@dataclass(frozen=True)
+class SdfMeta:
+    grid: GridMeta
+    multires: int
+    n_hidden: int
+    d_out: int
+
+    @property
+    def d_in(self):
+        return 3 + 6 * self.multires + self.grid.L * self.grid.C
+
+
+@dataclass(frozen=True)
+class ColorMeta:
+    grid: GridMeta      # grid.L == 0: no color grid
+    multires_view: int
+    feature: int
+    n_hidden: int
+    detached: bool
+
+    @property
+    def d_in(self):
+        return 3 + (3 + 6 * self.multires_view) + 3 + self.feature + self.grid.L * self.grid.C
+
+
+def _grid_struct(g, table, offsets):
+    s = GridT()
+    s.table = ptr(table, name="embeddings") if table is not None else None
+    s.offsets = ptr(offsets, torch.int32, "offsets") if offsets is not None else None
+    s.L, s.C, s.H, s.S, s.divide_factor = g.L, g.C, g.H, float(g.S), float(g.divide_factor)
+    return s
+
+
+def _sdf_struct(meta, table, offsets, wb):
+    n = meta.n_hidden
+    assert len(wb) == 2 * (n + 1)
+    s = SdfNetT()
+    s.grid = _grid_struct(meta.grid, table, offsets)
+    s.multires, s.n_hidden, s.d_out = meta.multires, n, meta.d_out
+    for l in range(n + 1):
+        s.W[l] = ptr(wb[2 * l], name=f"W{l}").value
+        s.b[l] = ptr(wb[2 * l + 1], name=f"b{l}").value
+    return s
+
+
+def _color_struct(meta, table, offsets, wb):
+    n = meta.n_hidden
+    assert len(wb) == 2 * (n + 1)
+    s = ColorNetT()
+    s.grid = _grid_struct(meta.grid, table, offsets)
+    s.multires_view, s.feature, s.n_hidden, s.grid_detached = meta.multires_view, meta.feature, n, int(meta.detached)
+    for l in range(n + 1):
+        s.W[l] = ptr(wb[2 * l], name=f"W{l}").value
+        s.b[l] = ptr(wb[2 * l + 1], name=f"b{l}").value
+    return s
+
+
+def _fm(t):
+    """[P, rows] tensor -> contiguous feature-major [rows, P] (no copy when t is a transposed view)."""
+    tt = t.t()
+    return tt if tt.is_contiguous() else tt.contiguous()
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def outer_accum(A, B, Cmat, bias=None):
+    """Cmat[M,N] += A[M,P] @ B[N,P]^T ; bias[M] += A.sum(1).  A, B feature-major (row stride = P)."""
+    M, P = A.shape
+    N = B.shape[0]
+    check(lib().nicer_outer_accum(ptr(A), A.stride(0), M, ptr(B), B.stride(0), N, P, ptr(Cmat), Cmat.stride(0),
+                                  ptr(bias) if bias is not None else None, stream()), "nicer_outer_accum")
+
+
+# --------------------------------------------------------------------------------------------- SDF network
+class SdfNetFn(torch.autograd.Function):
+    """(x, table, W0,b0,...,Wn,bn) -> (sdf [P,1], feat [P,F] (view of [F,P]), grad [P,3])."""
+
+    @staticmethod
+    def forward(ctx, x, table, offsets, meta, want_feat, *wb):
+        x = _c(x.detach())
+        wb = tuple(_c(t.detach()) for t in wb)
+        table_d = table.detach()
+        P = x.shape[0]
+        n = meta.n_hidden
+        dev = x.device
+        sdf = torch.empty(P, device=dev)
+        feat_fm = torch.empty(HIDDEN, P, device=dev) if want_feat else None
+        grad = torch.empty(P, 3, device=dev)
+        Z = torch.empty(n * HIDDEN, P, device=dev)
+        R = torch.empty((n - 1) * HIDDEN, P, device=dev) if n > 1 else None
+        DYDX = torch.empty(meta.grid.L * 3 * meta.grid.C, P, device=dev)
+        net = _sdf_struct(meta, table_d, offsets, wb)
+        flags = 0 if want_feat else F_NO_FEAT
+        check(lib().nicer_sdf_forward(C.byref(net), ptr(x), P, flags, ptr(sdf), ptr(feat_fm), ptr(grad), ptr(Z),
+                                      ptr(R), ptr(DYDX), stream()), "nicer_sdf_forward")
+        ctx.meta, ctx.want_feat = meta, want_feat
+        ctx.save_for_backward(x, table_d, offsets, Z, R, DYDX, *wb)
+        ctx.set_materialize_grads(False)
+        nfeat = meta.d_out - 1
+        feat = feat_fm[:nfeat].t() if want_feat else torch.zeros(P, 0, device=dev)
+        return sdf.view(P, 1), feat, grad
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_feat, g_grad):
+        x, table, offsets, Z, R, DYDX, *wb = ctx.saved_tensors
+        meta = ctx.meta
+        n, P, dev = meta.n_hidden, x.shape[0], x.device
+        nfeat = meta.d_out - 1
+        gs = _c(g_sdf.reshape(P)) if g_sdf is not None else None
+        gf = None
+        if g_feat is not None and ctx.want_feat:
+            gf = _fm(g_feat)
+            if nfeat < HIDDEN:
+                pad = torch.zeros(HIDDEN, P, device=dev)
+                pad[:nfeat] = gf
+                gf = pad
+        gg = _c(g_grad) if g_grad is not None else None
+        grad_x = torch.zeros(P, 3, device=dev) if ctx.needs_input_grad[0] else None
+        grad_table = torch.zeros_like(table)
+        ZB = torch.empty(n * HIDDEN, P, device=dev)
+        QB, AB, TAN = torch.empty_like(ZB), torch.empty_like(ZB), torch.empty_like(ZB)
+        H0 = torch.empty(meta.d_in, P, device=dev)
+        T0 = torch.empty(meta.d_in, P, device=dev)
+        net = _sdf_struct(meta, table, offsets, wb)
+        check(lib().nicer_sdf_backward(C.byref(net), ptr(x), P, ptr(Z), ptr(R), ptr(DYDX), ptr(gs), ptr(gf), ptr(gg),
+                                       ptr(grad_x), ptr(grad_table), ptr(ZB), ptr(QB), ptr(AB), ptr(TAN), ptr(H0),
+                                       ptr(T0), stream()), "nicer_sdf_backward")
+        grads = []
+        for l in range(n + 1):
+            W = wb[2 * l]
+            dW, db = torch.zeros_like(W), torch.zeros(W.shape[0], device=dev)
+            if l == 0:
+                outer_accum(ZB[:HIDDEN], H0, dW, db)
+                outer_accum(QB[:HIDDEN], T0, dW)
+            elif l < n:
+                outer_accum(ZB[l * HIDDEN:(l + 1) * HIDDEN], AB[(l - 1) * HIDDEN:l * HIDDEN], dW, db)
+                outer_accum(QB[l * HIDDEN:(l + 1) * HIDDEN], TAN[(l - 1) * HIDDEN:l * HIDDEN], dW)
+            else:
+                a_n = AB[(n - 1) * HIDDEN:]
+                if gs is not None:
+                    outer_accum(gs.view(1, P), a_n, dW[:1], db[:1])
+                if gf is not None and nfeat > 0:
+                    outer_accum(gf[:nfeat], a_n, dW[1:], db[1:])
+                dW[0] += TAN[(n - 1) * HIDDEN:].sum(dim=1)
+            grads += [dW, db]
+        return (grad_x, grad_table, None, None, None, *grads)
+
+
+def sdf_values(x, nets, out=None):
+    """No-grad SDF of the sum of networks (get_sdf_vals; the sampler's 640-sample pass).
+    nets: list of (meta, table, offsets, wb)."""
+    x = _c(x.detach())
+    P = x.shape[0]
+    sdf = out if out is not None else torch.empty(P, device=x.device)
+    for i, (meta, table, offsets, wb) in enumerate(nets):
+        wb = tuple(_c(t.detach()) for t in wb)
+        net = _sdf_struct(meta, table.detach(), offsets, wb)
+        flags = F_SDF_ONLY | (F_ACCUMULATE if i > 0 else 0)
+        check(lib().nicer_sdf_forward(C.byref(net), ptr(x), P, flags, ptr(sdf), None, None, None, None, None,
+                                      stream()), "nicer_sdf_forward")
+    return sdf.view(P, 1)
+
+
+# --------------------------------------------------------------------------------------------- color network
+class ColorNetFn(torch.autograd.Function):
+    """(x, view, normals, feat [P,F], table, W..,b..) -> rgb [P,3]."""
+
+    @staticmethod
+    def forward(ctx, x, view, normals, feat, table, offsets, meta, *wb):
+        x, view, normals = _c(x.detach()), _c(view.detach()), _c(normals.detach())
+        feat_fm = _fm(feat.detach())
+        wb = tuple(_c(t.detach()) for t in wb)
+        table_d = table.detach() if table is not None else None
+        P, dev, n = x.shape[0], x.device, meta.n_hidden
+        has_grid = table_d is not None
+        want_dx = has_grid and (not meta.detached) and ctx.needs_input_grad[0]
+        rgb = torch.empty(P, 3, device=dev)
+        A_fm = torch.empty(n * HIDDEN, P, device=dev)
+        DYDX = torch.empty(meta.grid.L * 3 * meta.grid.C, P, device=dev) if want_dx else None
+        net = _color_struct(meta, table_d, offsets, wb)
+        check(lib().nicer_color_forward(C.byref(net), ptr(x), ptr(view), ptr(normals), ptr(feat_fm), P, ptr(rgb),
+                                        ptr(A_fm), ptr(DYDX), stream()), "nicer_color_forward")
+        ctx.meta, ctx.has_grid = meta, has_grid
+        ctx.save_for_backward(x, view, normals, feat_fm, table_d, offsets, rgb, A_fm, DYDX, *wb)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        x, view, normals, feat_fm, table, offsets, rgb, A_fm, DYDX, *wb = ctx.saved_tensors
+        meta = ctx.meta
+        P, dev, n = x.shape[0], x.device, meta.n_hidden
+        g_rgb = _c(g_rgb)
+        grad_x = torch.zeros(P, 3, device=dev) if ctx.needs_input_grad[0] else None
+        grad_view = torch.empty(P, 3, device=dev) if ctx.needs_input_grad[1] else None
+        grad_normals = torch.empty(P, 3, device=dev)
+        grad_feat_fm = torch.empty(meta.feature, P, device=dev)
+        scatter = ctx.has_grid and not meta.detached
+        grad_table = torch.zeros_like(table) if scatter else None
+        ZB = torch.empty(n * HIDDEN, P, device=dev)
+        OB = torch.empty(3, P, device=dev)
+        H0 = torch.empty(meta.d_in, P, device=dev)
+        net = _color_struct(meta, table, offsets, wb)
+        check(lib().nicer_color_backward(C.byref(net), ptr(x), ptr(view), ptr(normals), ptr(feat_fm), P, ptr(rgb),
+                                         ptr(A_fm), ptr(DYDX), ptr(g_rgb), ptr(grad_x), ptr(grad_view),
+                                         ptr(grad_normals), ptr(grad_feat_fm), ptr(grad_table), ptr(ZB), ptr(OB),
+                                         ptr(H0), stream()), "nicer_color_backward")
+        grads = []
+        for l in range(n + 1):
+            W = wb[2 * l]
+            dW, db = torch.zeros_like(W), torch.zeros(W.shape[0], device=dev)
+            if l == 0:
+                outer_accum(ZB[:HIDDEN], H0, dW, db)
+            elif l < n:
+                outer_accum(ZB[l * HIDDEN:(l + 1) * HIDDEN], A_fm[(l - 1) * HIDDEN:l * HIDDEN], dW, db)
+            else:
+                outer_accum(OB, A_fm[(n - 1) * HIDDEN:], dW, db)
+            grads += [dW, db]
+        return (grad_x, grad_view, grad_normals, grad_feat_fm.t(), grad_table, None, None, *grads)
+
+
+# --------------------------------------------------------------------------------------------- compositing
+class CompositeFn(torch.autograd.Function):
+    """(sdf [P,1], x [P,3], z [R,S], rgb [P,3], grad [P,3], voxels) ->
+    (weights [R,S], rgb_values [R,3], depth [R,1], normal_map [R,3] (before rotation))."""
+
+    @staticmethod
+    def forward(ctx, sdf, x, z, rgb, grad, voxels):
+        R, S = z.shape
+        sdf_, x_, z_, rgb_, grad_ = (_c(t.detach()) for t in (sdf.reshape(-1), x, z, rgb, grad))
+        vox = _c(voxels.detach())
+        dev = z.device
+        weights = torch.empty(R, S, device=dev)
+        rgb_out = torch.empty(R, 3, device=dev)
+        depth = torch.empty(R, device=dev)
+        normal = torch.empty(R, 3, device=dev)
+        wsum = torch.empty(R, device=dev)
+        check(lib().nicer_composite_forward(ptr(sdf_), ptr(x_), ptr(z_), ptr(rgb_), ptr(grad_), ptr(vox), vox.shape[0],
+                                            R, S, ptr(weights), ptr(rgb_out), ptr(depth), ptr(normal), ptr(wsum),
+                                            stream()), "nicer_composite_forward")
+        ctx.save_for_backward(sdf_, x_, z_, rgb_, grad_, vox, weights, depth, wsum)
+        ctx.set_materialize_grads(False)
+        ctx.sdf_shape = sdf.shape
+        return weights, rgb_out, depth.view(R, 1), normal
+
+    @staticmethod
+    def backward(ctx, g_w, g_rgb_out, g_depth, g_normal):
+        sdf_, x_, z_, rgb_, grad_, vox, weights, depth, wsum = ctx.saved_tensors
+        R, S = z_.shape
+        dev = z_.device
+        g_sdf = torch.empty(R * S, device=dev)
+        g_rgb = torch.empty(R * S, 3, device=dev)
+        g_grad = torch.empty(R * S, 3, device=dev)
+        opt = lambda t: ptr(_c(t)) if t is not None else None  # noqa: E731
+        gd = _c(g_depth.reshape(R)) if g_depth is not None else None
+        check(lib().nicer_composite_backward(ptr(sdf_), ptr(x_), ptr(z_), ptr(rgb_), ptr(grad_), ptr(vox),
+                                             vox.shape[0], R, S, ptr(weights), ptr(depth), ptr(wsum), opt(g_rgb_out),
+                                             ptr(gd), opt(g_normal), opt(g_w), ptr(g_sdf), ptr(g_rgb), ptr(g_grad),
+                                             stream()), "nicer_composite_backward")
+        return g_sdf.view(ctx.sdf_shape), None, None, g_rgb, g_grad, None
+
+
+def sampler_weights(sdf, x, z, voxels):
+    R, S = z.shape
+    w = torch.empty(R, S, device=z.device)
+    vox = _c(voxels)
+    check(lib().nicer_sampler_weights(ptr(_c(sdf.reshape(-1))), ptr(_c(x)), ptr(_c(z)), ptr(vox), vox.shape[0], R, S,
+                                      ptr(w), stream()), "nicer_sampler_weights")
+    return w
+
+
+def voxel_count(x, voxels):
+    """In-place: voxels[cell(x)] += 1 for points with all |x_i| <= 0.99 (SLAMNetwork.update_voxels)."""
+    x = _c(x.detach())
+    check(lib().nicer_voxel_count(ptr(x), x.shape[0], ptr(voxels), voxels.shape[0], stream()), "nicer_voxel_count")
+
+
+# --------------------------------------------------------------------------------------------- drop-in hash op
+class _HashEncode(torch.autograd.Function):
+    """hashencoder/hashgrid.py:13-69 on top of the C-ABI drop-in op (reference layouts)."""
+
+    @staticmethod
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False):
+        inputs, embeddings, offsets = _c(inputs), _c(embeddings), _c(offsets)
+        B, D = inputs.shape
+        L, Cc = offsets.shape[0] - 1, embeddings.shape[1]
+        S, H = float(np.log2(per_level_scale)), int(base_resolution)
+        outputs = torch.empty(L, B, Cc, device=inputs.device)
+        dy_dx = torch.empty(B, L * D * Cc, device=inputs.device) if calc_grad_inputs else torch.empty(1, device=inputs.device)
+        check(lib().nicer_hash_encode_forward(ptr(inputs), ptr(embeddings), ptr(offsets, torch.int32), ptr(outputs), B,
+                                              D, Cc, L, S, H, int(calc_grad_inputs), ptr(dy_dx), stream()),
+              "nicer_hash_encode_forward")
+        ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
+        ctx.dims = (B, D, Cc, L, S, H, bool(calc_grad_inputs))
+        return outputs.permute(1, 0, 2).reshape(B, L * Cc)
+
+    @staticmethod
+    def backward(ctx, grad):
+        inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
+        B, D, Cc, L, S, H, cgi = ctx.dims
+        grad = grad.view(B, L, Cc).permute(1, 0, 2).contiguous()
+        gi, ge = _HashEncodeBackward.apply(grad, inputs, embeddings, offsets, dy_dx, ctx.dims)
+        return (gi if cgi else None), ge, None, None, None, None
+
+
+class _HashEncodeBackward(torch.autograd.Function):
+    """hashencoder/hashgrid.py:79-134: first backward as a differentiable op; its backward is K4+K5."""
+
+    @staticmethod
+    def forward(ctx, grad, inputs, embeddings, offsets, dy_dx, dims):
+        B, D, Cc, L, S, H, cgi = dims
+        grad_inputs = torch.zeros_like(inputs)
+        grad_embeddings = torch.zeros_like(embeddings)
+        check(lib().nicer_hash_encode_backward(ptr(grad), ptr(inputs), ptr(embeddings), ptr(offsets, torch.int32),
+                                               ptr(grad_embeddings), B, D, Cc, L, S, H, int(cgi), ptr(dy_dx),
+                                               ptr(grad_inputs), stream()), "nicer_hash_encode_backward")
+        ctx.save_for_backward(grad, inputs, embeddings, offsets, dy_dx)
+        ctx.dims = dims
+        return grad_inputs, grad_embeddings
+
+    @staticmethod
+    def backward(ctx, ggi, _gge):
+        grad, inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
+        B, D, Cc, L, S, H, cgi = ctx.dims
+        if not cgi:
+            raise RuntimeError("hash_encode: second backward requires calc_grad_inputs (dy_dx was not computed)")
+        grad_grad = torch.zeros_like(grad)
+        grad2_embeddings = torch.zeros_like(embeddings)
+        check(lib().nicer_hash_encode_second_backward(ptr(grad), ptr(inputs), ptr(embeddings),
+                                                      ptr(offsets, torch.int32), B, D, Cc, L, S, H, int(cgi), ptr(dy_dx),
+                                                      ptr(_c(ggi)), ptr(grad_grad), ptr(grad2_embeddings), stream()),
+              "nicer_hash_encode_second_backward")
+        return grad_grad, None, grad2_embeddings, None, None, None
+
+
+hash_encode = _HashEncode.apply

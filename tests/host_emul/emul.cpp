@@ -1,0 +1,306 @@
+// TEST INFRASTRUCTURE ONLY.  Host (g++) build of the per-point device functions in
+// nicer_slam_b200/csrc/*_sample.cuh behind the same C ABI as libnicer_b200.so, so that on a box
+// without a GPU the CPU test-suite can (1) check the kernels' math against the oracle and (2) run
+// the Python host layer (autograd wiring, buffer layouts) end to end on CPU tensors.
+// The product never loads this library: nicer_slam_b200/_lib.py only ever opens libnicer_b200.so
+// and raises if it is missing; tests/conftest.py swaps the handle explicitly for the CPU tests.
+#include <stdarg.h>
+#include <stdio.h>
+#include <vector>
+
+#include "../../include/nicer_b200.h"
+#include "../../nicer_slam_b200/csrc/color_sample.cuh"
+#include "../../nicer_slam_b200/csrc/composite_math.cuh"
+
+using namespace nicer;
+
+static thread_local char g_err[512] = "";
+static int fail(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return -1;
+}
+extern "C" const char *nicer_last_error(void) { return g_err; }
+extern "C" int nicer_version(void) { return -1; }   // negative: emulation
+
+namespace {
+struct HostSdf {
+    std::vector<float> W0t, Wt[3], WLt, wl_sdf, b0, b[3], bl_feat;
+    std::vector<LevelInfo> lv;
+    SdfNetView nv;
+    explicit HostSdf(const nicer_sdf_net_t &net) {
+        const int n = net.n_hidden, L = net.grid.L, C = net.grid.C;
+        const int d_pe = 3 + 6 * net.multires, d_in = d_pe + L * C;
+        W0t.assign(COL_ROWS * NICER_W, 0.f);
+        for (int j = 0; j < NICER_W; ++j) for (int k = 0; k < d_in; ++k) W0t[k * NICER_W + j] = net.W[0][j * d_in + k];
+        for (int l = 1; l < n; ++l) {
+            Wt[l - 1].assign(NICER_W * NICER_W, 0.f); b[l - 1].assign(NICER_W, 0.f);
+            for (int j = 0; j < NICER_W; ++j) { b[l - 1][j] = net.b[l][j]; for (int k = 0; k < NICER_W; ++k) Wt[l - 1][k * NICER_W + j] = net.W[l][j * NICER_W + k]; }
+        }
+        const int nfeat = net.d_out - 1;
+        WLt.assign(NICER_W * NICER_W, 0.f); wl_sdf.assign(NICER_W, 0.f); b0.assign(NICER_W, 0.f); bl_feat.assign(NICER_W, 0.f);
+        for (int j = 0; j < nfeat; ++j) for (int k = 0; k < NICER_W; ++k) WLt[k * NICER_W + j] = net.W[n][(1 + j) * NICER_W + k];
+        for (int i = 0; i < NICER_W; ++i) { wl_sdf[i] = net.W[n][i]; b0[i] = net.b[0][i]; if (i < nfeat) bl_feat[i] = net.b[n][1 + i]; }
+        for (int l = 0; l < L; ++l) lv.push_back(make_level(net.grid.offsets, l, net.grid.S, net.grid.H));
+        nv.W0t = W0t.data();
+        for (int i = 0; i < 3; ++i) { nv.Wt[i] = Wt[i].data(); nv.b[i] = b[i].data(); }
+        nv.WLt = WLt.data(); nv.wl_sdf = wl_sdf.data(); nv.b0 = b0.data(); nv.bl_feat = bl_feat.data();
+        nv.bl_sdf = net.b[n][0]; nv.lv = lv.data(); nv.table = net.grid.table;
+        nv.L = L; nv.n_hidden = n; nv.multires = net.multires; nv.d_pe = d_pe; nv.d_in = d_in; nv.df = net.grid.divide_factor;
+    }
+};
+
+struct HostColor {
+    std::vector<float> W0t, Wt[3], WL, b0, b[3];
+    std::vector<LevelInfo> lv;
+    ColorNetView nv;
+    explicit HostColor(const nicer_color_net_t &net) {
+        const int n = net.n_hidden;
+        const bool hg = net.grid.table != nullptr;
+        const int L = hg ? net.grid.L : 0, C = hg ? net.grid.C : 0;
+        const int d_view = 3 + 6 * net.multires_view, F = net.feature, d_in = 3 + d_view + 3 + F + L * C;
+        W0t.assign(160 * NICER_W, 0.f);
+        for (int j = 0; j < NICER_W; ++j) for (int k = 0; k < d_in; ++k) W0t[k * NICER_W + j] = net.W[0][j * d_in + k];
+        for (int l = 1; l < n; ++l) {
+            Wt[l - 1].assign(NICER_W * NICER_W, 0.f); b[l - 1].assign(NICER_W, 0.f);
+            for (int j = 0; j < NICER_W; ++j) { b[l - 1][j] = net.b[l][j]; for (int k = 0; k < NICER_W; ++k) Wt[l - 1][k * NICER_W + j] = net.W[l][j * NICER_W + k]; }
+        }
+        WL.assign(net.W[n], net.W[n] + 3 * NICER_W); b0.assign(net.b[0], net.b[0] + NICER_W);
+        for (int l = 0; l < L; ++l) lv.push_back(make_level(net.grid.offsets, l, net.grid.S, net.grid.H));
+        nv.W0t = W0t.data();
+        for (int i = 0; i < 3; ++i) { nv.Wt[i] = Wt[i].data(); nv.b[i] = b[i].data(); }
+        nv.WL = WL.data(); nv.b0 = b0.data();
+        nv.bl[0] = net.b[n][0]; nv.bl[1] = net.b[n][1]; nv.bl[2] = net.b[n][2];
+        nv.lv = lv.data(); nv.table = net.grid.table; nv.L = L; nv.n_hidden = n; nv.multires_view = net.multires_view;
+        nv.d_view = d_view; nv.feature = F; nv.d_in = d_in; nv.off_normal = 3 + d_view; nv.off_feat = 3 + d_view + 3;
+        nv.off_grid = 3 + d_view + 3 + F; nv.df = hg ? net.grid.divide_factor : 1.0f; nv.detached = net.grid_detached != 0;
+    }
+};
+}  // namespace
+
+#define DISPATCH_C(C, CALL)            \
+    switch (C) {                       \
+        case 2: { constexpr int CC = 2; CALL; } break; \
+        case 4: { constexpr int CC = 4; CALL; } break; \
+        case 8: { constexpr int CC = 8; CALL; } break; \
+        default: return fail("bad C"); \
+    }
+
+extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf,
+                                 float *feat_fm, float *grad, float *Z, float *R, float *DYDX, void *) {
+    HostSdf h(*net);
+    float col[COL_ROWS];
+    for (uint32_t p = 0; p < P; ++p)
+        DISPATCH_C(net->grid.C, (sdf_forward_sample<CC>(h.nv, x, p, P, flags, col, 1, sdf, feat_fm, grad, Z, R, DYDX)));
+    return 0;
+}
+
+extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
+                                  const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
+                                  const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
+                                  float *AB, float *TAN, float *H0, float *T0, void *) {
+    HostSdf h(*net);
+    float col[COL_ROWS];
+    for (uint32_t p = 0; p < P; ++p)
+        DISPATCH_C(net->grid.C, (sdf_backward_sample<CC>(h.nv, x, p, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x,
+                                                         grad_table, ZB, QB, AB, TAN, H0, T0, col, 1)));
+    return 0;
+}
+
+extern "C" int nicer_color_forward(const nicer_color_net_t *net, const float *x, const float *view,
+                                   const float *normals, const float *feat_fm, uint32_t P, float *rgb, float *A_fm,
+                                   float *DYDX, void *) {
+    HostColor h(*net);
+    float col[NICER_W];
+    const uint32_t C = net->grid.table ? net->grid.C : 2;
+    for (uint32_t p = 0; p < P; ++p)
+        DISPATCH_C(C, (color_forward_sample<CC>(h.nv, x, view, normals, feat_fm, p, P, col, 1, rgb, A_fm, DYDX)));
+    return 0;
+}
+
+extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x, const float *view,
+                                    const float *normals, const float *feat_fm, uint32_t P, const float *rgb,
+                                    const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
+                                    float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table,
+                                    float *ZB, float *OB, float *H0, void *) {
+    HostColor h(*net);
+    float col[NICER_W];
+    const uint32_t C = net->grid.table ? net->grid.C : 2;
+    for (uint32_t p = 0; p < P; ++p)
+        DISPATCH_C(C, (color_backward_sample<CC>(h.nv, x, view, normals, feat_fm, p, P, rgb, A_fm, DYDX, g_rgb, grad_x,
+                                                grad_view, grad_normals, grad_feat_fm, grad_table, ZB, OB, H0, col, 1)));
+    return 0;
+}
+
+extern "C" int nicer_outer_accum(const float *A, uint32_t lda, uint32_t M, const float *B, uint32_t ldb, uint32_t N,
+                                 uint32_t P, float *C, uint32_t ldc, float *bias, void *) {
+    for (uint32_t m = 0; m < M; ++m) {
+        for (uint32_t n = 0; n < N; ++n) {
+            double s = 0;
+            for (uint32_t p = 0; p < P; ++p) s += (double)A[(size_t)m * lda + p] * B[(size_t)n * ldb + p];
+            C[(size_t)m * ldc + n] += (float)s;
+        }
+        if (bias) { double s = 0; for (uint32_t p = 0; p < P; ++p) s += A[(size_t)m * lda + p]; bias[m] += (float)s; }
+    }
+    return 0;
+}
+
+static void ray_forward(const float *sdf, const float *X, const float *Z, const float *voxels, int res, uint32_t r,
+                        uint32_t S, std::vector<float> &E, std::vector<float> &T, std::vector<float> &beta) {
+    float carry = 0.f;
+    for (uint32_t i = 0; i < S; ++i) {
+        const size_t p = (size_t)r * S + i;
+        beta[i] = beta_lookup(voxels, res, X[3 * p], X[3 * p + 1], X[3 * p + 2]);
+        const float sigma = laplace_density(sdf[p], beta[i]);
+        const float delta = (i + 1 < S) ? (Z[p + 1] - Z[p]) : 1e10f;
+        E[i] = delta * sigma;
+        T[i] = expf(-carry);
+        carry += E[i];
+    }
+}
+
+extern "C" int nicer_composite_forward(const float *sdf, const float *x, const float *z, const float *rgb,
+                                       const float *grad, const float *voxels, uint32_t res, uint32_t R, uint32_t S,
+                                       float *weights, float *rgb_out, float *depth_out, float *normal_out,
+                                       float *wsum, void *) {
+    std::vector<float> E(S), T(S), beta(S);
+    for (uint32_t r = 0; r < R; ++r) {
+        ray_forward(sdf, x, z, voxels, (int)res, r, S, E, T, beta);
+        float aw = 0, awz = 0, ac[3] = {0, 0, 0}, an[3] = {0, 0, 0};
+        for (uint32_t i = 0; i < S; ++i) {
+            const size_t p = (size_t)r * S + i;
+            const float w = (1.0f - expf(-E[i])) * T[i];
+            weights[p] = w;
+            if (!rgb_out) continue;
+            aw += w; awz += w * z[p];
+            const float *g = grad + 3 * p;
+            const float den = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) + 1e-6f;
+            for (int c = 0; c < 3; ++c) { ac[c] += w * rgb[3 * p + c]; an[c] += w * (g[c] / den); }
+        }
+        if (rgb_out) {
+            wsum[r] = aw; depth_out[r] = awz / (aw + 1e-8f);
+            for (int c = 0; c < 3; ++c) { rgb_out[3 * r + c] = ac[c]; normal_out[3 * r + c] = an[c]; }
+        }
+    }
+    return 0;
+}
+
+extern "C" int nicer_sampler_weights(const float *sdf, const float *x, const float *z, const float *voxels,
+                                     uint32_t res, uint32_t R, uint32_t S, float *weights, void *st) {
+    return nicer_composite_forward(sdf, x, z, nullptr, nullptr, voxels, res, R, S, weights, nullptr, nullptr, nullptr,
+                                   nullptr, st);
+}
+
+extern "C" int nicer_composite_backward(const float *sdf, const float *x, const float *z, const float *rgb,
+                                        const float *grad, const float *voxels, uint32_t res, uint32_t R, uint32_t S,
+                                        const float *weights, const float *depth_out, const float *wsum,
+                                        const float *g_rgb_out, const float *g_depth_out, const float *g_normal_out,
+                                        const float *g_weights, float *g_sdf, float *g_rgb, float *g_grad, void *) {
+    std::vector<float> E(S), T(S), beta(S);
+    for (uint32_t r = 0; r < R; ++r) {
+        ray_forward(sdf, x, z, voxels, (int)res, r, S, E, T, beta);
+        float go_rgb[3] = {0, 0, 0}, go_n[3] = {0, 0, 0};
+        for (int c = 0; c < 3; ++c) { if (g_rgb_out) go_rgb[c] = g_rgb_out[3 * r + c]; if (g_normal_out) go_n[c] = g_normal_out[3 * r + c]; }
+        const float go_d = g_depth_out ? g_depth_out[r] : 0.f, dep = depth_out[r], inv_ws = 1.0f / (wsum[r] + 1e-8f);
+        float suffix = 0.f;
+        for (int i = (int)S - 1; i >= 0; --i) {
+            const size_t p = (size_t)r * S + i;
+            const float delta = ((uint32_t)i + 1 < S) ? (z[p + 1] - z[p]) : 1e10f;
+            const float w = weights[p];
+            const float wbar = composite_wbar(go_rgb, go_n, go_d, rgb + 3 * p, grad + 3 * p, z[p], dep, inv_ws,
+                                              g_weights ? g_weights[p] : 0.f);
+            composite_sample_backward(suffix, wbar, T[i], expf(-E[i]), delta, sdf[p], beta[i], w, go_rgb, go_n,
+                                      grad + 3 * p, g_sdf + p, g_rgb + 3 * p, g_grad + 3 * p);
+            suffix += -wbar * w;
+        }
+    }
+    return 0;
+}
+
+extern "C" int nicer_voxel_count(const float *X, uint32_t P, float *voxels, uint32_t res, void *) {
+    for (uint32_t p = 0; p < P; ++p) {
+        const float x = X[3 * (size_t)p], y = X[3 * (size_t)p + 1], z = X[3 * (size_t)p + 2];
+        if (fabsf(x) > 0.99f || fabsf(y) > 0.99f || fabsf(z) > 0.99f) continue;
+        const int ix = (int)((x + 1.0f) / 2.0f * (float)res), iy = (int)((y + 1.0f) / 2.0f * (float)res),
+                  iz = (int)((z + 1.0f) / 2.0f * (float)res);
+        voxels[((size_t)ix * res + iy) * res + iz] += 1.0f;
+    }
+    return 0;
+}
+
+// ---- drop-in hash op (D == 3 only in the emulation), via the shared nicer_math.cuh helpers
+template <int C>
+static void hash_fwd(const float *in, const float *emb, const int32_t *off, float *out, uint32_t B, uint32_t L, float S,
+                     uint32_t H, int dx, float *dy_dx) {
+    for (uint32_t l = 0; l < L; ++l) {
+        const LevelInfo li = make_level(off, l, S, H);
+        for (uint32_t b = 0; b < B; ++b) {
+            float feat[C], df[3][C];
+            if (dx) encode_level<C, true>(emb, li, in + 3 * (size_t)b, feat, df);
+            else encode_level<C, false>(emb, li, in + 3 * (size_t)b, feat, df);
+            for (int c = 0; c < C; ++c) out[((size_t)l * B + b) * C + c] = feat[c];
+            if (dx) for (int d = 0; d < 3; ++d) for (int c = 0; c < C; ++c) dy_dx[(((size_t)b * L + l) * 3 + d) * C + c] = df[d][c];
+        }
+    }
+}
+
+template <int C>
+static void hash_bwd(const float *grad, const float *in, const int32_t *off, float *gg, uint32_t B, uint32_t L, float S,
+                     uint32_t H, const float *ggx /* NULL: first order */) {
+    for (uint32_t l = 0; l < L; ++l) {
+        const LevelInfo li = make_level(off, l, S, H);
+        for (uint32_t b = 0; b < B; ++b) {
+            Cell3 cell = locate3(li, in + 3 * (size_t)b);
+            if (!cell.inside) continue;
+            uint32_t idx[8]; corner_indices(li, cell, idx);
+            float wt[8];
+            if (!ggx) corner_weights(cell, wt);
+            else {
+                float d0[8], d1[8], d2[8];
+                corner_dweights(cell, 0, d0); corner_dweights(cell, 1, d1); corner_dweights(cell, 2, d2);
+                for (int k = 0; k < 8; ++k) wt[k] = d0[k] * ggx[3 * (size_t)b] + d1[k] * ggx[3 * (size_t)b + 1] + d2[k] * ggx[3 * (size_t)b + 2];
+            }
+            for (int k = 0; k < 8; ++k) {
+                float v[C];
+                for (int c = 0; c < C; ++c) v[c] = wt[k] * grad[((size_t)l * B + b) * C + c];
+                scatter_entry<C>(gg, li, idx[k], v);
+            }
+        }
+    }
+}
+
+extern "C" int nicer_hash_encode_forward(const float *inputs, const float *embeddings, const int32_t *offsets,
+                                         float *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                                         uint32_t H, int calc_grad_inputs, float *dy_dx, void *) {
+    if (D != 3) return fail("emulation: D must be 3");
+    DISPATCH_C(C, (hash_fwd<CC>(inputs, embeddings, offsets, outputs, B, L, S, H, calc_grad_inputs, dy_dx)));
+    return 0;
+}
+
+extern "C" int nicer_hash_encode_backward(const float *grad, const float *inputs, const float *, const int32_t *offsets,
+                                          float *grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                                          uint32_t H, int calc_grad_inputs, const float *dy_dx, float *grad_inputs, void *) {
+    if (D != 3) return fail("emulation: D must be 3");
+    DISPATCH_C(C, (hash_bwd<CC>(grad, inputs, offsets, grad_embeddings, B, L, S, H, nullptr)));
+    if (calc_grad_inputs)
+        for (uint32_t b = 0; b < B; ++b) for (int d = 0; d < 3; ++d) {
+            float r = 0;
+            for (uint32_t l = 0; l < L; ++l) for (uint32_t c = 0; c < C; ++c)
+                r += grad[((size_t)l * B + b) * C + c] * dy_dx[(((size_t)b * L + l) * 3 + d) * C + c];
+            grad_inputs[3 * (size_t)b + d] = r;
+        }
+    return 0;
+}
+
+extern "C" int nicer_hash_encode_second_backward(const float *grad, const float *inputs, const float *,
+                                                 const int32_t *offsets, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                                                 float S, uint32_t H, int, const float *dy_dx, const float *ggx,
+                                                 float *grad_grad, float *grad2_embeddings, void *) {
+    if (D != 3) return fail("emulation: D must be 3");
+    for (uint32_t l = 0; l < L; ++l) for (uint32_t b = 0; b < B; ++b) for (uint32_t c = 0; c < C; ++c) {
+        float r = 0;
+        for (int d = 0; d < 3; ++d) r += ggx[3 * (size_t)b + d] * dy_dx[(((size_t)b * L + l) * 3 + d) * C + c];
+        grad_grad[((size_t)l * B + b) * C + c] = r;
+    }
+    DISPATCH_C(C, (hash_bwd<CC>(grad, inputs, offsets, grad2_embeddings, B, L, S, H, ggx)));
+    return 0;
+}
