@@ -1,0 +1,223 @@
+"""SLAMNetwork with the reference's constructor / forward contract and output dictionary
+(/root/reference/code/model/network.py:14-370), running the per-iteration volume-rendering step on the
+fused sm_100a kernels:
+
+    rays (torch, differentiable w.r.t. pose) -> sampler (fused sdf-only + density/transmittance kernels)
+    -> SDF nets (one fused kernel per net: gather + PE + MLP + d sdf/dx) -> color net (fused)
+    -> density + compositing (warp-scan kernel) -> depth / normal maps, flow, warp, eikonal samples.
+
+Drop-in: ``train.model_class = "nicer_slam_b200.model.network.SLAMNetwork"`` in the conf.
+Multi-GPU (ray-parallel): see nicer_slam_b200/parallel.py.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..utils import rend_util
+from ..utils.general import uv2patch
+from .base_networks import ImplicitNetworkGrid_COMBINE, RenderingNetwork
+from .density import GridPredefineDensity, LaplaceDensity
+from .ray_sampler import DeviceRng, ImportantSampler
+
+
+class SLAMNetwork(nn.Module):
+    def __init__(self, conf, dataset=None, n_images=2000):
+        super().__init__()
+        self.dataset = dataset
+        self.H, self.W = self.dataset.img_res
+        self.white_bkgd = conf.get_bool("white_bkgd", default=False)
+        self.feature_vector_size = conf.get_int("feature_vector_size")
+        self.use_warp_loss = conf.get_bool("use_warp_loss", default=False)
+        self.embedding_method = conf.get_string("embedding_method", default="nerf")
+        self.mapping_patchsizes = conf.get_list("mapping_patchsizes", default=[1, 5, 11])
+        self.tracking_patchsizes = conf.get_list("tracking_patchsizes", default=[1, 5, 11])
+        self.patchsizes = self.mapping_patchsizes
+        self.scene_bounding_sphere = conf.get_float("scene_bounding_sphere", default=1.0)
+        self.register_buffer("bg_color", torch.tensor(conf.get_list("bg_color", default=[1.0, 1.0, 1.0])).float(),
+                             persistent=False)
+        self.implicit_network = ImplicitNetworkGrid_COMBINE(
+            conf.get_config("implicit_network"), self.feature_vector_size,
+            0.0 if self.white_bkgd else self.scene_bounding_sphere)
+        self.rendering_network = RenderingNetwork(
+            self.feature_vector_size, n_images=n_images, embedding_method=self.embedding_method,
+            **conf.get_config("rendering_network"))
+        self.density_method = conf.get_string("density_method", default="volsdf_gridpredefined")
+        if self.density_method == "volsdf_laplace":
+            self.density = LaplaceDensity(**conf.get_config("density"))
+        elif self.density_method == "volsdf_gridpredefined":
+            self.density = GridPredefineDensity(**conf.get_config("gridpredefinedensity"))
+        else:
+            raise NotImplementedError(self.density_method)
+        sampling_method = conf.get_string("sampling_method", default="important")
+        if sampling_method != "important":
+            raise NotImplementedError
+        self.ray_sampler = ImportantSampler(self.scene_bounding_sphere, **conf.get_config("ray_sampler"))
+        self.sampling_method = sampling_method
+        # voxel visit counter: mutable model state saved in checkpoints by the trainer (volsdf_train.py:227)
+        self.voxel_res = conf.get_int("voxel_res", default=64)
+        self.register_buffer("voxels", torch.zeros(self.voxel_res, self.voxel_res, self.voxel_res), persistent=False)
+        self.voxels_shape = self.voxels.shape
+        self.rng = DeviceRng()
+        self._sync_density_voxels()
+
+    def _sync_density_voxels(self):
+        if "gridpredefined" in self.density_method:
+            self.density.voxels = self.voxels
+            self.density.voxel_res = self.voxel_res
+
+    def update_voxels(self, x):
+        """Histogram the main-pass points into the 64^3 counter (network.py:62-76), in place."""
+        if not self.voxels.is_contiguous():
+            self.voxels = self.voxels.contiguous()
+        ops.voxel_count(x, self.voxels)
+        self._sync_density_voxels()
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, input, indices, ground_truth, keyframe_list=None, frame_idx=-1, mode="vis", stage="fine",
+                color_stage="highfreq", iter=0):
+        if mode == "tracking":
+            self.patchsizes = self.tracking_patchsizes
+        elif mode == "mapping":
+            self.patchsizes = self.mapping_patchsizes
+        self._sync_density_voxels()
+
+        intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
+        ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
+        eye = torch.eye(4, device=pose.device, dtype=pose.dtype)[None].repeat(pose.shape[0], 1, 1)
+        depth_scale = rend_util.get_camera_params(uv, eye, intrinsics)[0][:, :, 2:]   # unnormalised z (F5)
+        bs, num_pixels, _ = ray_dirs.shape
+        batch_size = bs
+        cam_loc = cam_loc.unsqueeze(1).repeat(1, num_pixels, 1).reshape(-1, 3)
+        ray_dirs = ray_dirs.reshape(-1, 3)
+
+        z_vals, z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self, frame_idx, keyframe_list, mode)
+        N_samples = z_vals.shape[1]
+        points = cam_loc.unsqueeze(1) + z_vals.unsqueeze(2) * ray_dirs.unsqueeze(1)
+        points_flat = points.reshape(-1, 3)
+        if mode == "mapping":
+            self.update_voxels(points_flat.detach())
+        dirs_flat = ray_dirs.unsqueeze(1).expand(-1, N_samples, -1).reshape(-1, 3)
+
+        sdf, feature_vectors, gradients = self.implicit_network.get_outputs(points_flat, stage=stage)
+        rgb_flat = self.rendering_network(points_flat, gradients, dirs_flat, feature_vectors, indices,
+                                          color_stage=color_stage)
+        rgb = rgb_flat.reshape(-1, N_samples, 3)
+
+        if isinstance(self.density, GridPredefineDensity):
+            weights, rgb_values, depth_values, normal_map = ops.CompositeFn.apply(
+                sdf, points_flat.detach(), z_vals, rgb_flat, gradients, self.voxels)
+        else:
+            weights = self.volume_rendering(z_vals, sdf, points_flat)
+            rgb_values = torch.sum(weights.unsqueeze(-1) * rgb, 1)
+            depth_values = torch.sum(weights * z_vals, 1, keepdims=True) / (weights.sum(dim=1, keepdims=True) + 1e-8)
+            normals = gradients / (gradients.norm(2, -1, keepdim=True) + 1e-6)
+            normal_map = torch.sum(weights.unsqueeze(-1) * normals.reshape(-1, N_samples, 3), 1)
+
+        rendered_depth = depth_values.unsqueeze(2)
+        surf = (cam_loc.unsqueeze(1) + rendered_depth * ray_dirs.unsqueeze(1)).reshape(bs, -1, 3).permute(0, 2, 1)
+
+        output = {}
+        if "edges" in ground_truth:   # optical-flow projection i -> j (network.py:153-165)
+            idii, idjj, _, _ = ground_truth["edges"]
+            w2c = torch.linalg.inv(pose[idjj])
+            cam_pts = w2c[:, :3, :3] @ surf[idii] + w2c[:, :3, 3:]
+            proj = (intrinsics[idjj][:, :3, :3] @ cam_pts).permute(0, 2, 1)
+            output["flow"] = proj[..., :2] / (proj[..., 2:] + 1e-8) - uv[idii]
+
+        if self.use_warp_loss and ("vis" not in mode) and ("tracking" not in mode):
+            output["warp_output"] = self._warp(uv, pose, intrinsics, rendered_depth, ground_truth, batch_size)
+
+        depth_values = depth_scale * depth_values.reshape(bs, -1, 1)
+        if self.white_bkgd:
+            acc_map = torch.sum(weights, -1)
+            rgb_values = rgb_values + (1.0 - acc_map[..., None]) * self.bg_color.unsqueeze(0)
+        output.update({
+            "rgb": rgb,
+            "rgb_values": rgb_values.reshape(bs, -1, 3),
+            "depth_values": depth_values,
+            "z_vals": z_vals,
+            "depth_vals": z_vals * depth_scale.reshape(-1, 1),
+            "sdf": sdf.reshape(z_vals.shape),
+            "weights": weights,
+            "entropy": (-weights * torch.log(weights + 1e-4)).sum(dim=-1).mean(),
+            "scene_bounding_sphere": self.scene_bounding_sphere,
+        })
+
+        if self.training and ("vis" not in mode) and ("mapping" in mode):
+            # eikonal samples: 10 uniform points per ray + one near-surface point per ray, each with a jittered
+            # neighbour (network.py:313-336)
+            n_eik = batch_size * num_pixels
+            dev = points_flat.device
+            eik = self.rng.eik_uniform(n_eik * 10, self.scene_bounding_sphere, dev)
+            with torch.no_grad():
+                near_surface = (cam_loc.unsqueeze(1) + z_samples_eik.unsqueeze(2) * ray_dirs.unsqueeze(1)).reshape(-1, 3)
+            eik = torch.cat([eik, near_surface], 0)
+            eik = torch.cat([eik, eik + (self.rng.eik_jitter(eik) - 0.5) * 0.01], 0)
+            grad_theta = self.implicit_network.gradient(eik, stage=stage)
+            half = grad_theta.shape[0] // 2
+            output["grad_theta"], output["grad_theta_nei"] = grad_theta[:half], grad_theta[half:]
+
+        normal_map = normal_map.reshape(bs, -1, 3)
+        output["normal_map"] = torch.einsum("bij,bni->bnj", pose[:, :3, :3], normal_map)
+        return output
+
+    # ------------------------------------------------------------------------------------------------
+    def _warp(self, uv, pose, intrinsics, rendered_depth, ground_truth, bs):
+        """Photometric warping of every frame's pixels (lifted with the rendered depth) into all frames of the batch
+        (network.py:167-279).  Returns {patchsize: (gt_rgb, sampled_rgb, mask, ray_level_depth_mask)}."""
+        H, W = self.H, self.W
+        full_rgb = ground_truth["full_rgb"].reshape(bs, H, W, 3)
+        full_depth = ground_truth["full_depth"].reshape(bs, H, W, 1)
+        depth = rendered_depth.reshape(bs, -1, 1, 1)
+        w2c = torch.linalg.inv(pose)
+        K3 = intrinsics[:, :3, :3]
+        out = {}
+        for ps in self.patchsizes:
+            pp = ps * ps
+            uv_patch = uv2patch(uv, ps).reshape(bs, -1, 2)
+            dirs_p, loc_p = rend_util.get_camera_params(uv_patch, pose, intrinsics)
+            pts = loc_p[:, None, None, :] + depth * dirs_p.reshape(bs, -1, pp, 3)
+            pts = pts.reshape(-1, 3).permute(1, 0)                                  # [3, bs*N*pp]
+            cam_pts = w2c[:, :3, :3] @ pts + w2c[:, :3, 3:]                          # [bs(target), 3, bs*N*pp]
+            proj = (K3 @ cam_pts).permute(0, 2, 1).reshape(bs, bs, -1, pp, 3)        # (target, reference, N, pp, 3)
+            t_depth = proj[..., 2:]
+            t_uv = proj[..., :2] / (t_depth + 1e-8)
+            t_uv = torch.stack([t_uv[..., 0] / W, t_uv[..., 1] / H], -1) * 2 - 1.0
+            t_uv = t_uv.reshape(bs, -1, 1, 2)
+            t_depth = t_depth.reshape(bs, -1, 1)
+            sampled = F.grid_sample(full_rgb.permute(0, 3, 1, 2), t_uv, mode="bilinear", padding_mode="zeros",
+                                    align_corners=True)
+            sampled = sampled.reshape(bs, 3, bs, -1, pp).permute(0, 2, 3, 4, 1)
+            s_mask = ((t_uv[..., 0] > -1) & (t_uv[..., 0] < 1) & (t_uv[..., 1] > -1) & (t_uv[..., 1] < 1)
+                      & (t_depth > 0)).reshape(bs, bs, -1, pp)
+            # ground-truth colour / depth of the patch pixels in their own frame (1 where outside the image)
+            u, v = uv_patch[..., 0], uv_patch[..., 1]
+            inside = (0 <= u) & (0 <= v) & (u < W) & (v < H)
+            ui, vi = u.long().clamp(0, W - 1), v.long().clamp(0, H - 1)
+            bi = torch.arange(bs, device=uv.device)[:, None].expand_as(ui)
+            gt_rgb = torch.where(inside[..., None], full_rgb[bi, vi, ui], torch.ones_like(full_rgb[bi, vi, ui]))
+            gt_depth = torch.where(inside[..., None], full_depth[bi, vi, ui], torch.ones_like(full_depth[bi, vi, ui]))
+            g_mask = inside.unsqueeze(0).repeat(bs, 1, 1).reshape(bs, bs, -1, pp)
+            gt_rgbs = gt_rgb.reshape(1, bs, -1, pp, 3).repeat(bs, 1, 1, 1, 1)
+            total = g_mask & s_mask
+            ray_level = None
+            if ps > 1:
+                d = gt_depth.reshape(bs, -1, pp)
+                flat_ok = torch.var(d, dim=-1, unbiased=False) < 0.01
+                ray_level = flat_ok.reshape(-1)
+                total = total & flat_ok.unsqueeze(0).unsqueeze(-1).repeat(bs, 1, 1, pp).reshape(bs, bs, -1, pp)
+            out[ps] = (gt_rgbs, sampled, total, ray_level)
+        return out
+
+    def volume_rendering(self, z_vals, sdf, points_flat, rays_o=None, rays_d=None, gradients=None, frame_idx=1,
+                         mode=None):
+        """Compositing weights (network.py:349-370).  With the voxel-counter density this is the fused kernel;
+        the learned-beta LaplaceDensity takes the elementwise path."""
+        if isinstance(self.density, GridPredefineDensity) and not torch.is_grad_enabled():
+            return ops.sampler_weights(sdf, points_flat, z_vals, self.voxels)
+        density = self.density(sdf, x=points_flat).reshape(-1, z_vals.shape[1])
+        dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full_like(z_vals[:, :1], 1e10)], -1)
+        free_energy = dists * density
+        shifted = torch.cat([torch.zeros_like(free_energy[:, :1]), free_energy[:, :-1]], dim=-1)
+        return (1 - torch.exp(-free_energy)) * torch.exp(-torch.cumsum(shifted, dim=-1))

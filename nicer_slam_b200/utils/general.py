@@ -1,0 +1,51 @@
+"""Hot-path helpers of the reference's utils/general.py: the plug-in resolver ``get_class`` (:153-159), the
+differentiable pose parametrisation ``quad2rotation`` / ``get_camera_from_tensor`` (:52-100),
+``uv2patch`` (:129-145) and ``index_to_1d`` (:31-36)."""
+import torch
+
+
+def get_class(kls):
+    parts = kls.split(".")
+    m = __import__(".".join(parts[:-1]))
+    for comp in parts[1:]:
+        m = getattr(m, comp)
+    return m
+
+
+def index_to_1d(x, s):
+    return x[:, 0] * s * s + x[:, 1] * s + x[:, 2]
+
+
+def quad2rotation(quad):
+    """[B,4] un-normalised quaternion (w,x,y,z) -> [B,3,3]; two_s = 2/|q|^2 keeps it differentiable for any norm."""
+    qr, qi, qj, qk = quad.unbind(-1)
+    two_s = 2.0 / (quad * quad).sum(-1)
+    rows = (
+        1 - two_s * (qj * qj + qk * qk), two_s * (qi * qj - qk * qr), two_s * (qi * qk + qj * qr),
+        two_s * (qi * qj + qk * qr), 1 - two_s * (qi * qi + qk * qk), two_s * (qj * qk - qi * qr),
+        two_s * (qi * qk - qj * qr), two_s * (qj * qk + qi * qr), 1 - two_s * (qi * qi + qj * qj),
+    )
+    return torch.stack(rows, -1).reshape(quad.shape[0], 3, 3)
+
+
+def get_camera_from_tensor(inputs):
+    """[7] or [B,7] (quat wxyz, translation) -> c2w [4,4] or [B,4,4]."""
+    single = inputs.dim() == 1
+    if single:
+        inputs = inputs.unsqueeze(0)
+    R = quad2rotation(inputs[:, :4])
+    RT = torch.cat([R, inputs[:, 4:, None]], 2)
+    bottom = torch.tensor([0.0, 0.0, 0.0, 1.0], device=RT.device, dtype=RT.dtype).expand(RT.shape[0], 1, 4)
+    RT = torch.cat([RT, bottom], 1)
+    return RT[0] if single else RT
+
+
+def uv2patch(uv, patchsize):
+    """Pixel centres [B,N,2] -> patch pixel coordinates [B,N,p,p,2]."""
+    if patchsize == 1:
+        return uv.clone().reshape(-1, uv.shape[1], 1, 1, 2)
+    half = patchsize // 2
+    r = torch.arange(-half, half + 1, device=uv.device)
+    gx, gy = torch.meshgrid(r, r, indexing="ij")
+    grid = torch.stack([gx, gy], -1)[None, None]
+    return uv[:, :, None, None, :] + grid

@@ -1,0 +1,145 @@
+"""CPU checks of the *device* per-point functions (csrc/*_sample.cuh, composite_math.cuh) compiled for the host
+(tests/host_emul) and of the whole Python host layer on top of them, against the oracle and the reference goldens.
+These do not replace the GPU parity tests (tests/test_gpu_*.py); they catch formula / layout bugs without a GPU."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from emul_util import emulated_library
+from nicer_slam_b200 import ops
+from oracle import render_oracle as ro
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _wb(layers):
+    out = []
+    for v, g, b in layers:
+        out += [torch._weight_norm(v, g, 0), b]
+    return out
+
+
+@pytest.mark.parametrize("hidden,L,C,logmap", [([64], 2, 8, 19), ([64, 64, 64], 4, 4, 10), ([64, 64], 8, 2, 8)])
+def test_sdf_net_first_and_second_order(hidden, L, C, logmap):
+    torch.manual_seed(0)
+    spec = ro.GridSpec(L, C, 4, 16, logmap)
+    net = ro.make_sdf_net(spec, hidden, 64, seed=3, table_scale=0.3)
+    P = 200
+    x0 = torch.rand(P, 3) * 2.1 - 1.05   # some points outside the grid
+    leaves = [net["table"]] + [t for l in net["layers"] for t in l]
+    for t in leaves:
+        t.requires_grad_(True)
+    x = x0.clone().requires_grad_(True)
+    sdf, feat, g = ro.sdf_net_outputs(x, net)
+    wS, wF, wG = torch.randn(P, 1), torch.randn(P, 64), torch.randn(P, 3)
+    want = torch.autograd.grad((sdf * wS).sum() + (feat * wF).sum() + (g * wG).sum(), [x] + leaves)
+    meta = ops.SdfMeta(ops.GridMeta(L, C, 4, float(np.log2(spec.pls)), 1.0), 6, len(hidden), 65)
+    with emulated_library():
+        x2 = x0.clone().requires_grad_(True)
+        tab = net["table"].detach().clone().requires_grad_(True)
+        vgb = [[t.detach().clone().requires_grad_(True) for t in l] for l in net["layers"]]
+        s2, f2, g2 = ops.SdfNetFn.apply(x2, tab, spec.offsets, meta, True, *_wb(vgb))
+        assert rel(s2, sdf) < 2e-6 and rel(f2, feat) < 2e-6 and rel(g2, g) < 5e-6
+        got = torch.autograd.grad((s2 * wS).sum() + (f2 * wF).sum() + (g2 * wG).sum(),
+                                  [x2, tab] + [t for l in vgb for t in l])
+        sv = ops.sdf_values(x0, [(meta, tab, spec.offsets, _wb(vgb))])
+        assert rel(sv, sdf) < 2e-6
+    for a, b in zip(got, want):
+        assert rel(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("stage", ["highfreq", "base"])
+def test_color_net(stage):
+    torch.manual_seed(1)
+    spec = ro.GridSpec(16, 2, 4, 48, 9)
+    net = ro.make_color_net(spec, [64, 64], 64, seed=5, table_scale=0.3)
+    P = 150
+    x0, v0, n0, f0 = torch.rand(P, 3) * 2.1 - 1.05, torch.randn(P, 3) * 0.7, torch.randn(P, 3), torch.randn(P, 64) * 0.5
+    leaves = [net["table"]] + [t for l in net["layers"] for t in l]
+    for t in leaves:
+        t.requires_grad_(True)
+    ins = [t.clone().requires_grad_(True) for t in (x0, v0, n0, f0)]
+    rgb = ro.color_net(ins[0], ins[2], ins[1], ins[3], net, stage)
+    wR = torch.randn(P, 3)
+    want = torch.autograd.grad((rgb * wR).sum(), ins + leaves, allow_unused=True)
+    meta = ops.ColorMeta(ops.GridMeta(16, 2, 4, float(np.log2(spec.pls)), 1.0), 4, 64, 2, stage == "base")
+    with emulated_library():
+        ins2 = [t.clone().requires_grad_(True) for t in (x0, v0, n0, f0)]
+        tab = net["table"].detach().clone().requires_grad_(True)
+        vgb = [[t.detach().clone().requires_grad_(True) for t in l] for l in net["layers"]]
+        rgb2 = ops.ColorNetFn.apply(*ins2, tab, spec.offsets, meta, *_wb(vgb))
+        assert rel(rgb2, rgb) < 2e-6
+        got = torch.autograd.grad((rgb2 * wR).sum(), ins2 + [tab] + [t for l in vgb for t in l], allow_unused=True)
+    for a, b in zip(got, want):
+        if b is None:
+            assert a is None or float(a.abs().max()) == 0.0
+        else:
+            assert rel(a, b) < 2e-5
+
+
+def test_composite_forward_backward():
+    R, S = 37, 45
+    gen = torch.Generator().manual_seed(1)
+    z, _ = torch.sort(torch.rand(R, S, generator=gen) * 2, -1)
+    o = torch.rand(R, 1, 3, generator=gen) * 0.5 - 0.25
+    d = torch.nn.functional.normalize(torch.randn(R, 1, 3, generator=gen), dim=-1)
+    xp = (o + z.unsqueeze(-1) * d).reshape(-1, 3)
+    sdf0, rgb0, g0 = torch.randn(R * S, 1, generator=gen) * 0.02, torch.rand(R * S, 3, generator=gen), torch.randn(R * S, 3, generator=gen)
+    vox = torch.poisson(torch.full((64, 64, 64), 50.0), generator=gen)
+
+    def oracle(sdf, rgb, g):
+        w = ro.render_weights(z, ro.laplace_density(sdf, ro.beta_from_voxels(xp, vox)).reshape(R, S))
+        n = g / (g.norm(2, -1, keepdim=True) + 1e-6)
+        return (w, (w.unsqueeze(-1) * rgb.reshape(R, S, 3)).sum(1), (w * z).sum(1, keepdim=True) / (w.sum(1, keepdim=True) + 1e-8),
+                (w.unsqueeze(-1) * n.reshape(R, S, 3)).sum(1))
+
+    ins = [t.clone().requires_grad_(True) for t in (sdf0, rgb0, g0)]
+    outs = oracle(*ins)
+    ws = [torch.randn_like(t) for t in outs]
+    want = torch.autograd.grad(sum((a * b).sum() for a, b in zip(outs, ws)), ins)
+    with emulated_library():
+        ins2 = [t.clone().requires_grad_(True) for t in (sdf0, rgb0, g0)]
+        o2 = ops.CompositeFn.apply(ins2[0], xp, z, ins2[1], ins2[2], vox)
+        for a, b in zip(o2, outs):
+            assert rel(a, b) < 1e-6
+        got = torch.autograd.grad(sum((a * b).sum() for a, b in zip(o2, ws)), ins2)
+        assert rel(ops.sampler_weights(sdf0, xp, z, vox), outs[0]) < 1e-6
+    for a, b in zip(got, want):
+        assert rel(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["step_tracking.npz", "step_mapping.npz", "step_mapping_coarse_base.npz"])
+def test_full_step_against_reference_goldens(name):
+    """Product SLAMNetwork + SLAMLoss + backward (host layer on the emulated kernels) vs the reference's outputs,
+    loss terms and gradients, with the reference's own z samples (frozen z)."""
+    fx, meta = gu.load_step(name)
+    with emulated_library():
+        model, _ = gu.build_model()
+        out, lo, gcam = gu.run_step(model, fx, meta, "cpu", frozen_z=True)
+    for k in ("rgb_values", "depth_values", "normal_map", "sdf", "weights", "rgb", "grad_theta", "grad_theta_nei", "flow"):
+        if "out." + k in fx:
+            assert rel(out[k], fx["out." + k]) < 1e-5, k
+    for k in lo:
+        assert abs(float(lo[k]) - float(fx["loss." + k])) <= 2e-5 * max(abs(float(fx["loss." + k])), 1e-3), k
+    named = dict(model.named_parameters())
+    for k in fx:
+        if k.startswith("grad.") and k != "grad.cam7":
+            assert rel(named[gu.ref_name(k[5:])].grad, fx[k]) < 1e-4, k
+    assert rel(gcam, fx["grad.cam7"]) < 1e-4
+    assert torch.equal(model.voxels, fx["voxels_after"])
+
+
+def test_free_running_sampler_close_to_reference():
+    """With the reference's random draws replayed, our sampler reproduces its z samples up to the 1/beta-amplified
+    fp32 reorder noise and the renders stay within 1e-4."""
+    fx, meta = gu.load_step("step_tracking.npz")
+    with emulated_library():
+        model, _ = gu.build_model()
+        out, lo, _ = gu.run_step(model, fx, meta, "cpu", frozen_z=False)
+    assert rel(out["z_vals"], fx["out.z_vals"]) < 2e-3
+    assert rel(out["rgb_values"], fx["out.rgb_values"]) < 1e-4
+    assert rel(out["depth_values"], fx["out.depth_values"]) < 1e-4
