@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the NICER-SLAM volume-rendering step (BASELINE.json metric:
+ray-samples/sec, forward+backward) on 1..8 B200s, plus roofline / CPU-baseline / end-to-end legs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]         our arm (torchrun launches N ranks for N > 1)
+  python bench.py --impl reference [...]                      the reference algorithm on the host cores (oracle port)
+
+A "step" is one mapping iteration of confs/runconf_demo_2.conf (BASELINE configs[1]): 16 frames x 256 pixels =
+4096 rays, S = 64+32+2 = 98 samples per ray (P = 401 408 ray-samples), 640-sample hierarchical sampler pass,
+eikonal pass (22 points per ray), full loss stack (RGB + warp + mono depth + mono normal + flow + eikonal +
+smoothness), backward to the three grids, all MLP weights and the 16 camera poses.  Synthetic inputs of that shape,
+seeded random weights (no dataset / checkpoint access).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H_IMG, W_IMG = 680, 1200
+N_SAMPLES, N_EVAL, N_EXTRA = 64, 640, 32
+S_MAIN = N_SAMPLES + N_EXTRA + 2
+
+# Algorithmic work per ray-sample: MLP FLOPs fwd 76 288 + SDF gradient pass 51 200 + backward 254 976
+FLOP_CORE_FULL = 382_464
+FLOP_CORE_SDF = 307_200
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------- synthetic workload
+def synth_cameras(n, gen):
+    """Cameras inside the unit cube looking roughly along +z with small random rotations / offsets."""
+    quat = torch.tensor([1.0, 0.0, 0.0, 0.0])[None].repeat(n, 1) + 0.05 * torch.randn(n, 4, generator=gen)
+    trans = 0.15 * torch.randn(n, 3, generator=gen) + torch.tensor([0.0, 0.0, -0.35])
+    return torch.cat([quat, trans], 1)
+
+
+def synth_inputs(rays, frames, gen, H=H_IMG, W=W_IMG, with_flow=True):
+    """Host tensors of one mapping batch in the trainer's layout (volsdf_train.py:500-545, scene_dataset.py:214-259)."""
+    npix = rays // frames
+    K = torch.eye(4)[None].repeat(frames, 1, 1)
+    K[:, 0, 0] = K[:, 1, 1] = 600.0 * W / 1200.0
+    K[:, 0, 2], K[:, 1, 2] = (W - 1) / 2, (H - 1) / 2
+    cam7 = synth_cameras(frames, gen)
+    sidx = torch.randint(H * W, (npix,), generator=gen)
+    uv = torch.stack([(sidx % W).float(), (sidx // W).float()], -1)[None].repeat(frames, 1, 1)
+    host = dict(K=K, cam7=cam7, uv=uv, sidx=sidx,
+                rgb=torch.rand(frames, npix, 3, generator=gen), mask=torch.ones(frames, npix, 1),
+                depth=torch.rand(frames, npix, 1, generator=gen),
+                normal=torch.nn.functional.normalize(torch.randn(frames, npix, 3, generator=gen), dim=-1),
+                gt_depth=torch.rand(frames, npix, 1, generator=gen) * 1.5 + 0.5)
+    if with_flow and frames >= 2:
+        ii = torch.arange(frames - 1)
+        host["edges"] = torch.stack([ii, ii + 1, ii * 10, (ii + 1) * 10])
+        host["flow"] = torch.randn(frames - 1, npix, 2, generator=gen) * 3
+        host["flow_mask"] = torch.rand(frames - 1, npix, generator=gen) > 0.3
+    return host
+
+
+def seed_weights(model, seed):
+    """Non-degenerate seeded weights (the geometric init zeroes the hash columns of lin0)."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("encoding.embeddings"):
+                p.copy_((torch.rand(p.shape, generator=gen) * 2 - 1) * 0.1)
+            elif name.endswith("weight_v"):
+                p.copy_(torch.randn(p.shape, generator=gen) * (math.sqrt(2) / math.sqrt(p.shape[0])))
+            elif name.endswith("weight_g"):
+                pass
+            elif name.endswith("bias"):
+                p.copy_(0.05 * torch.randn(p.shape, generator=gen))
+        for mod in model.modules():
+            if hasattr(mod, "weight_g") and hasattr(mod, "weight_v"):
+                scale = 0.3 if mod.weight_v.shape[0] == 65 else 1.0     # small SDF range so rays cross the surface
+                mod.weight_v.mul_(scale)
+                mod.weight_g.copy_(mod.weight_v.norm(2, dim=1, keepdim=True))
+    model.voxels.copy_(torch.poisson(torch.full(model.voxels.shape, 50.0), generator=gen))
+
+
+class Step:
+    """One mapping iteration through the reference-facing API (SLAMNetwork.forward + SLAMLoss + backward)."""
+
+    def __init__(self, model, loss, host, frames, device, full_frames):
+        from nicer_slam_b200.utils.general import get_camera_from_tensor
+        self.model, self.loss, self.host, self.frames, self.device = model, loss, host, frames, device
+        self._cam = get_camera_from_tensor
+        self.full = full_frames                      # device-resident frame cache (full_rgb / full_depth)
+        self.pinned = {k: (v.pin_memory() if device != "cpu" and torch.cuda.is_available() else v) for k, v in host.items()}
+        self.dev = {k: v.to(device) for k, v in host.items()}
+        self.cam7 = self.dev["cam7"].clone().requires_grad_(True)
+        self.rays = host["uv"].shape[0] * host["uv"].shape[1]
+
+    def _gt(self, src):
+        gt = {k: src[k] for k in ("rgb", "mask", "depth", "normal", "gt_depth")}
+        gt.update(self.full)
+        if "edges" in src:
+            e = src["edges"]
+            gt["edges"] = (e[0], e[1], e[2], e[3])
+            gt["flow"], gt["flow_mask"] = src["flow"], src["flow_mask"]
+        return gt
+
+    def run(self, src=None, sl=slice(None)):
+        """forward + loss + backward with inputs already on the device. Returns the loss tensor."""
+        src = src or self.dev
+        self.model.zero_grad(set_to_none=True)
+        self.cam7.grad = None
+        inp = {"intrinsics": src["K"], "uv": src["uv"], "pose": self._cam(self.cam7), "sampling_idx": src["sidx"]}
+        idx = torch.arange(self.frames, device=self.device)
+        out = self.model(inp, idx, self._gt(src), keyframe_list=list(range(self.frames)), frame_idx=5, mode="mapping",
+                         stage="fine", color_stage="highfreq")
+        lo = self.loss(out, self._gt(src), list(range(self.frames)), frame_idx=5, stage="fine")
+        lo["loss"].backward()
+        return lo["loss"]
+
+    def run_e2e(self):
+        """Same step through the public API with HOST buffers: pinned H2D of the step inputs, D2H of the loss."""
+        src = {k: v.to(self.device, non_blocking=True) for k, v in self.pinned.items()}
+        loss = self.run(src)
+        return float(loss.item())
+
+    def h2d_bytes(self):
+        return int(sum(v.numel() * v.element_size() for v in self.pinned.values()))
+
+    def forward_only(self):
+        with torch.no_grad():
+            self.model.eval()
+            inp = {"intrinsics": self.dev["K"], "uv": self.dev["uv"], "pose": self._cam(self.cam7.detach()), "sampling_idx": self.dev["sidx"]}
+            out = self.model(inp, torch.arange(self.frames, device=self.device), self._gt(self.dev), mode="mapping_vis")
+            self.model.train()
+        return out
+
+    def grad_of_rgb_sum(self, frame_slice):
+        """d(sum rgb_values)/d(MLP weights) for a subset of frames (deterministic sampler: eval mode)."""
+        self.model.zero_grad(set_to_none=True)
+        self.model.eval()
+        sub = {k: (v[frame_slice] if k in ("K", "uv", "cam7") else v) for k, v in self.dev.items()}
+        n = sub["K"].shape[0]
+        inp = {"intrinsics": sub["K"], "uv": sub["uv"], "pose": self._cam(sub["cam7"]), "sampling_idx": sub["sidx"]}
+        out = self.model(inp, torch.arange(n, device=self.device), {}, mode="mapping_vis")
+        out["rgb_values"].sum().backward()
+        self.model.train()
+        return {k: p.grad.clone() for k, p in self.model.named_parameters() if p.grad is not None and "lin" in k}
+
+
+def build_step(rays=4096, frames=16, color_logmap=24, device="cuda", seed=0, H=H_IMG, W=W_IMG):
+    from nicer_slam_b200.model.base_networks import RenderingNetwork
+    from nicer_slam_b200.model.loss import SLAMLoss
+    from nicer_slam_b200.model.network import SLAMNetwork
+    from nicer_slam_b200.utils.conf import DEMO2_LOSS, demo2_model_conf
+
+    class DS:
+        img_res = [H, W]
+        data_dir = "synthetic"
+
+    saved = dict(RenderingNetwork.COLOR_GRID)
+    RenderingNetwork.COLOR_GRID = dict(saved, logmap=color_logmap)
+    try:
+        model = SLAMNetwork(demo2_model_conf(N_SAMPLES, N_EVAL, N_EXTRA), dataset=DS(), n_images=200)
+    finally:
+        RenderingNetwork.COLOR_GRID = saved
+    seed_weights(model, seed + 1)
+    model = model.to(device).train()
+    loss = SLAMLoss(trainer=None, train_dataset=DS(), scan_id=2, model=model, **DEMO2_LOSS)
+    gen = torch.Generator().manual_seed(seed + 2)
+    host = synth_inputs(rays, frames, gen, H, W)
+    full = {"full_rgb": torch.rand(frames, H * W, 3, generator=gen).to(device),
+            "full_depth": (torch.rand(frames, H * W, 1, generator=gen) * 1.5 + 0.5).to(device)}
+    return Step(model, loss, host, frames, device, full)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+                 "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.f.flush()
+            self.f.seek(0)
+            self.rows = [r.strip().split(", ") for r in self.f.read().strip().splitlines() if r.strip()]
+            self.f.close()
+            os.unlink(self.f.name)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm / cpu baseline
+def cpu_reference_step(rays, frames, seed, color_logmap, threads):
+    """The reference algorithm on the host cores: oracle/render_oracle.py (torch CPU restatement, pinned to the
+    reference by tests/golden) + oracle/hashgrid_oracle.c.  Returns a callable running one fwd+loss+bwd step."""
+    from nicer_slam_b200.utils.conf import DEMO2_LOSS
+    from oracle import render_oracle as ro
+    torch.set_num_threads(threads)
+    cs, fs = ro.GridSpec(4, 8, 32, 32, 19), ro.GridSpec(8, 4, 32, 128, 19)
+    ks = ro.GridSpec(16, 2, 16, 2048, color_logmap)
+    params = {"coarse": ro.make_sdf_net(cs, [64], 64, seed=seed + 1), "fine": ro.make_sdf_net(fs, [64, 64, 64], 64, seed=seed + 2),
+              "color": ro.make_color_net(ks, [64, 64], 64, seed=seed + 3)}
+    gen = torch.Generator().manual_seed(seed + 4)
+    params["voxels"] = torch.poisson(torch.full((64, 64, 64), 50.0), generator=gen)
+    leaves = ro.leaf_params(params)
+    H, W = 68, 120   # small frames for the warp lookups only; ray geometry uses the same normalised intrinsics
+    host = synth_inputs(rays, frames, gen, H, W)
+    gt = {k: host[k] for k in ("rgb", "mask", "depth", "normal", "gt_depth")}
+    gt["full_rgb"] = torch.rand(frames, H * W, 3, generator=gen)
+    gt["full_depth"] = torch.rand(frames, H * W, 1, generator=gen) * 1.5 + 0.5
+    if "edges" in host:
+        e = host["edges"]
+        gt["edges"], gt["flow"], gt["flow_mask"] = (e[0], e[1], e[2], e[3]), host["flow"], host["flow_mask"]
+    cfg = dict(near=0.0, N_samples=N_SAMPLES, N_samples_eval=N_EVAL, N_samples_extra=N_EXTRA, scene_bounding_sphere=1.0,
+               H=H, W=W, use_warp_loss=True, mapping_patchsizes=[1], tracking_patchsizes=[1])
+    cam7 = host["cam7"].clone().requires_grad_(True)
+
+    def step():
+        for t in leaves.values():
+            t.grad = None
+        cam7.grad = None
+        out = ro.render_forward({"intrinsics": host["K"], "uv": host["uv"], "pose": ro.camera_from_tensor(cam7)}, gt,
+                                params, cfg, "mapping", "fine", "highfreq", training=True)
+        lo = ro.slam_loss(out, gt, DEMO2_LOSS, frame_idx=5, stage="fine")
+        lo["loss"].backward()
+        return float(lo["loss"])
+    return step
+
+
+def time_cpu(rays, frames, steps, warmup, color_logmap=19):
+    threads = os.cpu_count() or 1
+    step = cpu_reference_step(rays, frames, 0, color_logmap, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return rays * S_MAIN / dt, dt, threads
+
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=4096)
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--color-logmap", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    workload = (f"runconf_demo_2 mapping iteration: {args.frames} frames x {args.rays // args.frames} px = {args.rays} rays, "
+                f"S={S_MAIN}, N_eval={N_EVAL}, eikonal 22/ray, full loss stack, stage=fine, color_stage=highfreq")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cpu_rays, cpu_frames = 256, 16
+        steps = min(args.steps, 3)
+        val, dt, threads = time_cpu(cpu_rays, cpu_frames, steps, min(args.warmup, 1))
+        sample = f"{cpu_rays} of the {args.rays} rays per step ({cpu_frames} frames x {cpu_rays // cpu_frames} px), color grid 2^19/level, {steps} steps"
+        line = {"impl": "reference", "metric": "ray-samples/sec fwd+bwd", "value": val, "unit": "ray-samples/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "l2": "inputs larger than L2 n/a (CPU)"},
+                "cpu_baseline": {"value": val, "unit": "ray-samples/s", "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch.distributed as dist
+    from nicer_slam_b200 import _lib
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    from nicer_slam_b200 import parallel
+
+    step = build_step(args.rays, args.frames, args.color_logmap, dev, seed=rank)
+    P = args.rays * S_MAIN
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)   # 192 MiB > 126 MB L2
+
+    def one(e2e=False):
+        flush.add_(1.0)                                         # L2 flush between timed iterations
+        v = step.run_e2e() if e2e else step.run()
+        if world > 1:
+            parallel.allreduce_gradients(step.model, extra=[step.cam7])
+        return v
+
+    for _ in range(max(args.warmup, 3)):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _lib.launch_count = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            one()
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count
+    # subtract nothing: the L2 flush is part of the timed region (it is ~0.06 ms per step)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * P / (ms_per_step * 1e-3)
+
+    # end-to-end leg: host buffers in, loss out
+    for _ in range(2):
+        one(e2e=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        one(e2e=True)
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = world * P / (float(e2e_ms.item()) * 1e-3)
+
+    extra = {}
+    if rank == 0 and not args.no_kernel_timing:
+        extra = kernel_breakdown(step, dev)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, threads = time_cpu(256, 16, 1, 1)
+        cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
+               "sample": "256 of the 4096 rays of one step (16 frames x 16 px), color grid 2^19/level, 1 timed step after 1 warm-up"}
+    if rank == 0:
+        peaks = _peaks()
+        line = {"metric": "ray-samples/sec fwd+bwd", "value": value, "unit": "ray-samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "rays_per_gpu": args.rays, "ray_samples_per_step_per_gpu": P,
+                           "color_grid_log2_entries": args.color_logmap, "parallelism": f"ray-parallel x{world}",
+                           "l2": "192 MiB flush buffer written between timed iterations; color grid (1 GB) > L2"},
+                "clocks": clk.summary(), "gpu_launches": launches,
+                "e2e": {"value": e2e_val, "unit": "ray-samples/s", "h2d_bytes_per_step": step.h2d_bytes(), "d2h_bytes_per_step": 4,
+                        "note": "frames (full_rgb/full_depth) are a device-resident cache; per-step uv/pose/K/sampled GT come from pinned host memory"}}
+        line.update(extra)
+        if "roofline" in line:
+            line["roofline"]["peak_source"] = peaks["source"]
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def kernel_breakdown(step, dev):
+    """CUDA-event timing of the individual fused kernels on the step's own main-pass points (core-SDF / core-full
+    figures of SURVEY.md 8d) and the roofline entry for the dominant kernel."""
+    from nicer_slam_b200 import ops
+    m = step.model
+    P = step.rays * S_MAIN
+    torch.manual_seed(0)
+    x = (torch.rand(P, 3, device=dev) * 2 - 1) * 0.9
+    view = torch.randn(P, 3, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def timed(fn, n=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    res = {}
+    coarse, fine, color = m.implicit_network.coarse, m.implicit_network.fine, m.rendering_network
+    gS, gF, gG = torch.randn(P, 1, device=dev), torch.randn(64, P, device=dev).t(), torch.randn(P, 3, device=dev)
+
+    def sdf_fb(net):
+        meta, table, off, wb = net.fused_args()
+        xs = x.clone().requires_grad_(True)
+        s, f, g = ops.SdfNetFn.apply(xs, table, off, meta, True, *wb)
+        torch.autograd.backward([s, f, g], [gS, gF, gG])
+    t_c, t_f = timed(lambda: sdf_fb(coarse)), timed(lambda: sdf_fb(fine))
+    res["core_sdf"] = {"ms": t_c + t_f, "ray_samples_per_s": P / ((t_c + t_f) * 1e-3),
+                       "tensor_tflops_algorithmic": P * FLOP_CORE_SDF / ((t_c + t_f) * 1e-3) / 1e12}
+
+    def color_fb():
+        xs = x.clone().requires_grad_(True)
+        nrm = gG.clone().requires_grad_(True)
+        ft = gF.clone().requires_grad_(True)
+        rgb = color(xs, nrm, view, ft, None, color_stage="highfreq")
+        rgb.backward(torch.ones_like(rgb))
+    t_col = timed(color_fb)
+    res["core_full"] = {"ms": t_c + t_f + t_col, "ray_samples_per_s": P / ((t_c + t_f + t_col) * 1e-3)}
+    # dominant kernel: fine SDF net forward+backward pair; algorithmic flops of that net (fwd 33 792 + grad 24 576*... see DESIGN.md)
+    flop_fine = 2 * (71 * 64 + 64 * 64 * 2 + 64 * 65) * 1 + 2 * (71 * 64 + 64 * 64 * 2 + 64) + 2 * 2 * (71 * 64 + 64 * 64 * 2 + 64 * 65) + 2 * 2 * (71 * 64 + 64 * 64 * 2 + 64)
+    peaks = _peaks()
+    ach = P * flop_fine / (t_f * 1e-3) / 1e12
+    res["roofline"] = {"bound": "tensor", "kernel": "sdf_forward_kernel<4> + sdf_backward_kernel<4> + outer_accum (fine SDF net, fwd+grad+bwd)",
+                       "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                       "traffic": None, "flop_per_sample": flop_fine, "ms_per_launch_group": t_f,
+                       "note": "v1 kernels are fp32 SIMT (no tensor cores yet); peak is the measured dense bf16 tensor rate"}
+    return res
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -50,6 +50,8 @@ _SIGS = {
 }
 
 _handle = None
+launch_count = 0          # kernels launched through this binding (bench.py's gpu_launches)
+_LAUNCHES = {"nicer_hash_encode_backward": 2}
 
 
 def _bind(h):
@@ -78,6 +80,8 @@ def exported_symbols():
 
 
 def check(rc, what=""):
+    global launch_count
+    launch_count += _LAUNCHES.get(what, 1)
     if rc != 0:
         msg = lib().nicer_last_error()
         raise RuntimeError(f"libnicer_b200 {what} failed ({rc}): {msg.decode() if msg else '?'}")
