@@ -27,7 +27,7 @@ static ColorSmemLayout color_layout(int n_hidden) {
     return s;
 }
 
-__device__ void stage_color_net(const nicer_color_net_t &net, const ColorSmemLayout &lay, float *smem, ColorNetView &nv) {
+__device__ void stage_color_net(const nicer_color_net_t &net, const LevelScales &ls, const ColorSmemLayout &lay, float *smem, ColorNetView &nv) {
     const int n = (int)net.n_hidden;
     const bool has_grid = net.grid.table != nullptr;
     const int L = has_grid ? (int)net.grid.L : 0, C = has_grid ? (int)net.grid.C : 0;
@@ -51,7 +51,7 @@ __device__ void stage_color_net(const nicer_color_net_t &net, const ColorSmemLay
     for (int i = tid; i < 3 * NICER_W; i += nt) smem[lay.WL + i] = net.W[n][i];
     for (int i = tid; i < NICER_W; i += nt) smem[lay.b0 + i] = net.b[0][i];
     LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
-    for (int l = tid; l < L; l += nt) lv[l] = make_level(net.grid.offsets, (uint32_t)l, net.grid.S, net.grid.H);
+    for (int l = tid; l < L; l += nt) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
     nv.W0t = W0t;
     for (int i = 0; i < 3; ++i) { nv.Wt[i] = smem + lay.Wt[i]; nv.b[i] = smem + lay.b[i]; }
     nv.WL = smem + lay.WL;
@@ -67,12 +67,12 @@ __device__ void stage_color_net(const nicer_color_net_t &net, const ColorSmemLay
 
 template <int C>
 __global__ void __launch_bounds__(COL_BLOCK, 2)
-color_forward_kernel(const nicer_color_net_t net, const ColorSmemLayout lay, const float *__restrict__ X,
+color_forward_kernel(const nicer_color_net_t net, const LevelScales ls, const ColorSmemLayout lay, const float *__restrict__ X,
                      const float *__restrict__ V, const float *__restrict__ N, const float *__restrict__ feat_fm,
                      uint32_t P, float *rgb, float *A_fm, float *DYDX) {
     extern __shared__ __align__(16) float smem[];
     ColorNetView nv;
-    stage_color_net(net, lay, smem, nv);
+    stage_color_net(net, ls, lay, smem, nv);
     __syncthreads();
     float *col = smem + lay.col + threadIdx.x;
     const uint32_t tiles = (P + COL_BLOCK - 1) / COL_BLOCK;
@@ -84,14 +84,14 @@ color_forward_kernel(const nicer_color_net_t net, const ColorSmemLayout lay, con
 
 template <int C>
 __global__ void __launch_bounds__(COL_BLOCK, 2)
-color_backward_kernel(const nicer_color_net_t net, const ColorSmemLayout lay, const float *__restrict__ X,
+color_backward_kernel(const nicer_color_net_t net, const LevelScales ls, const ColorSmemLayout lay, const float *__restrict__ X,
                       const float *__restrict__ V, const float *__restrict__ N, const float *__restrict__ feat_fm,
                       uint32_t P, const float *rgb, const float *A_fm, const float *DYDX, const float *g_rgb,
                       float *grad_x, float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table,
                       float *ZB, float *OB, float *H0) {
     extern __shared__ __align__(16) float smem[];
     ColorNetView nv;
-    stage_color_net(net, lay, smem, nv);
+    stage_color_net(net, ls, lay, smem, nv);
     __syncthreads();
     float *col = smem + lay.col + threadIdx.x;
     const uint32_t tiles = (P + COL_BLOCK - 1) / COL_BLOCK;
@@ -132,6 +132,7 @@ extern "C" int nicer_color_forward(const nicer_color_net_t *net, const float *x,
     if (P == 0) return 0;
     if (!x || !view || !normals || !feat_fm || !rgb || !A_fm) NICER_FAIL(-1, "nicer_color_forward: NULL pointer");
     ColorSmemLayout lay = color_layout((int)net->n_hidden);
+    const LevelScales ls = host_level_scales(net->grid.table ? net->grid.L : 0, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);
     const uint32_t tiles = div_up(P, COL_BLOCK);
     const uint32_t grid = tiles < (uint32_t)(2 * num_sms()) ? tiles : (uint32_t)(2 * num_sms());
@@ -141,7 +142,7 @@ extern "C" int nicer_color_forward(const nicer_color_net_t *net, const float *x,
     do {                                                                                                             \
         NICER_CUDA(cudaFuncSetAttribute(color_forward_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
                    "nicer_color_forward");                                                                           \
-        color_forward_kernel<CC><<<grid, COL_BLOCK, smem, st>>>(*net, lay, x, view, normals, feat_fm, P, rgb, A_fm, DYDX); \
+        color_forward_kernel<CC><<<grid, COL_BLOCK, smem, st>>>(*net, ls, lay, x, view, normals, feat_fm, P, rgb, A_fm, DYDX); \
     } while (0)
     switch (C) {
         case 2: LAUNCH(2); break;
@@ -165,6 +166,7 @@ extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x
     if (net->grid.table && !net->grid_detached && !grad_table)
         NICER_FAIL(-1, "nicer_color_backward: grad_table required when the grid is not detached");
     ColorSmemLayout lay = color_layout((int)net->n_hidden);
+    const LevelScales ls = host_level_scales(net->grid.table ? net->grid.L : 0, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);
     const uint32_t tiles = div_up(P, COL_BLOCK);
     const uint32_t grid = tiles < (uint32_t)(2 * num_sms()) ? tiles : (uint32_t)(2 * num_sms());
@@ -174,7 +176,7 @@ extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x
     do {                                                                                                              \
         NICER_CUDA(cudaFuncSetAttribute(color_backward_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
                    "nicer_color_backward");                                                                           \
-        color_backward_kernel<CC><<<grid, COL_BLOCK, smem, st>>>(*net, lay, x, view, normals, feat_fm, P, rgb, A_fm, DYDX, \
+        color_backward_kernel<CC><<<grid, COL_BLOCK, smem, st>>>(*net, ls, lay, x, view, normals, feat_fm, P, rgb, A_fm, DYDX, \
                                                                   g_rgb, grad_x, grad_view, grad_normals, grad_feat_fm, \
                                                                   grad_table, ZB, OB, H0);                            \
     } while (0)

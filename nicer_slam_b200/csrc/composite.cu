@@ -27,6 +27,16 @@ __device__ __forceinline__ float warp_incl_scan_rev(float v, int lane) {
     }
     return v;
 }
+// Exclusive prefix / suffix sums computed from the SHIFTED values (never as inclusive - self: the last sample of a
+// ray has a free energy of ~1e10*sigma and subtracting it back would cancel the whole prefix in fp32).
+__device__ __forceinline__ float warp_excl_scan(float v, int lane) {
+    float prev = __shfl_up_sync(0xffffffffu, v, 1);
+    return warp_incl_scan(lane == 0 ? 0.f : prev, lane);
+}
+__device__ __forceinline__ float warp_excl_scan_rev(float v, int lane) {
+    float next = __shfl_down_sync(0xffffffffu, v, 1);
+    return warp_incl_scan_rev(lane == 31 ? 0.f : next, lane);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -54,8 +64,8 @@ composite_forward_kernel(const float *__restrict__ sdf, const float *__restrict_
         const float zi = Z[p];
         const float delta = (i + 1 < S) ? (Z[p + 1] - zi) : 1e10f;
         const float E = valid ? delta * sigma : 0.f;
-        const float incl = warp_incl_scan(E, lane);
-        const float excl = incl - E + carry;
+        const float pre = warp_excl_scan(E, lane);
+        const float excl = pre + carry;
         const float T = expf(-excl);
         const float alpha = 1.0f - expf(-E);
         const float w = valid ? alpha * T : 0.f;
@@ -69,7 +79,7 @@ composite_forward_kernel(const float *__restrict__ sdf, const float *__restrict_
             const float den = sqrtf(gx * gx + gy * gy + gz * gz) + 1e-6f;
             a_n[0] += w * (gx / den); a_n[1] += w * (gy / den); a_n[2] += w * (gz / den);
         }
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        carry += __shfl_sync(0xffffffffu, pre + E, 31);
     }
     if (FULL) {
         a_w = warp_sum(a_w); a_wz = warp_sum(a_wz);
@@ -130,8 +140,7 @@ composite_backward_kernel(const float *__restrict__ sdf, const float *__restrict
         const float zi = Z[p];
         const float delta = (i + 1 < S) ? (Z[p + 1] - zi) : 1e10f;
         const float E = valid ? delta * sigma : 0.f;
-        const float incl = warp_incl_scan(E, lane);
-        const float excl = incl - E + carries[wrp][ch];
+        const float excl = warp_excl_scan(E, lane) + carries[wrp][ch];
         const float T = expf(-excl);
         const float eE = expf(-E);
         const float w = valid ? weights[p] : 0.f;
@@ -139,8 +148,8 @@ composite_backward_kernel(const float *__restrict__ sdf, const float *__restrict
         const float cvec[3] = {rgb[3 * p], rgb[3 * p + 1], rgb[3 * p + 2]};
         float wbar = valid ? composite_wbar(go_rgb, go_n, go_d, cvec, gvec, zi, dep, inv_ws, g_weights ? g_weights[p] : 0.f) : 0.f;
         const float cbar = -wbar * w;                       // dL/d(prefix_i) = -wbar_i * alpha_i * T_i
-        const float sincl = warp_incl_scan_rev(cbar, lane);
-        const float sexcl = sincl - cbar + rcarry;          // sum over samples after i
+        const float spre = warp_excl_scan_rev(cbar, lane);
+        const float sexcl = spre + rcarry;                   // sum over samples after i
         if (valid) {
             float gs, gc[3], gg[3];
             composite_sample_backward(sexcl, wbar, T, eE, delta, s, beta, w, go_rgb, go_n, gvec, &gs, gc, gg);
@@ -148,7 +157,7 @@ composite_backward_kernel(const float *__restrict__ sdf, const float *__restrict
 #pragma unroll
             for (int c = 0; c < 3; ++c) { g_rgb[3 * p + c] = gc[c]; g_grad[3 * p + c] = gg[c]; }
         }
-        rcarry += __shfl_sync(0xffffffffu, sincl, 0);
+        rcarry += __shfl_sync(0xffffffffu, spre + cbar, 0);
     }
 }
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ Cell<D> locate(const LevelInfo &li, const float *x) {
     for (uint32_t d = 0; d < D; ++d) {
         float v = x[d];
         if (v < 0.f || v > 1.f) c.inside = false;
-        float p = v * li.scale;
+        float p = __fmul_rn(v, li.scale);   // not contracted with the subtraction below
         c.pg[d] = (uint32_t)floorf(p);
         p -= (float)c.pg[d];
         c.dw[d] = sstep_d(p);
@@ -96,12 +96,12 @@ __device__ __forceinline__ void vec_red(float *dst, const float v[C]) {
 template <uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256)
 hash_forward_kernel(const float *__restrict__ inputs, const float *__restrict__ grid, const int *__restrict__ offsets,
-                    float *__restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, bool want_dx,
+                    float *__restrict__ outputs, uint32_t B, uint32_t L, const LevelScales ls, bool want_dx,
                     float *__restrict__ dy_dx) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
-    const LevelInfo li = make_level(offsets, level, S, H);
+    const LevelInfo li = make_level(offsets, level, ls.s[level]);
     const float *tab = grid + (size_t)li.offset * C;
     const Cell<D> c = locate<D>(li, inputs + (size_t)b * D);
     float *out = outputs + ((size_t)level * B + b) * C;
@@ -159,11 +159,11 @@ hash_forward_kernel(const float *__restrict__ inputs, const float *__restrict__ 
 template <uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256)
 hash_backward_kernel(const float *__restrict__ grad, const float *__restrict__ inputs, const int *__restrict__ offsets,
-                     float *__restrict__ grad_grid, uint32_t B, uint32_t L, float S, uint32_t H) {
+                     float *__restrict__ grad_grid, uint32_t B, uint32_t L, const LevelScales ls) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
-    const LevelInfo li = make_level(offsets, level, S, H);
+    const LevelInfo li = make_level(offsets, level, ls.s[level]);
     const Cell<D> c = locate<D>(li, inputs + (size_t)b * D);
     if (!c.inside) return;
     float g[C];
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256)
 hash_second_backward_kernel(const float *__restrict__ grad, const float *__restrict__ inputs,
                             const int *__restrict__ offsets, const float *__restrict__ dy_dx,
                             const float *__restrict__ ggx, float *__restrict__ grad_grad,
-                            float *__restrict__ grad2_grid, uint32_t B, uint32_t L, float S, uint32_t H) {
+                            float *__restrict__ grad2_grid, uint32_t B, uint32_t L, const LevelScales ls) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
@@ -238,7 +238,7 @@ hash_second_backward_kernel(const float *__restrict__ grad, const float *__restr
         }
         vec_store<C>(grad_grad + ((size_t)level * B + b) * C, r);
     }
-    const LevelInfo li = make_level(offsets, level, S, H);
+    const LevelInfo li = make_level(offsets, level, ls.s[level]);
     const Cell<D> c = locate<D>(li, inputs + (size_t)b * D);
     if (!c.inside) return;
     float g[C];
@@ -269,11 +269,12 @@ hash_second_backward_kernel(const float *__restrict__ grad, const float *__restr
 template <uint32_t D>
 static int launch_forward(uint32_t C, dim3 g, cudaStream_t st, const float *in, const float *emb, const int *off,
                           float *out, uint32_t B, uint32_t L, float S, uint32_t H, bool dx, float *dy_dx) {
+    const LevelScales ls = host_level_scales(L, S, H);
     switch (C) {
-        case 1: hash_forward_kernel<D, 1><<<g, 256, 0, st>>>(in, emb, off, out, B, L, S, H, dx, dy_dx); break;
-        case 2: hash_forward_kernel<D, 2><<<g, 256, 0, st>>>(in, emb, off, out, B, L, S, H, dx, dy_dx); break;
-        case 4: hash_forward_kernel<D, 4><<<g, 256, 0, st>>>(in, emb, off, out, B, L, S, H, dx, dy_dx); break;
-        case 8: hash_forward_kernel<D, 8><<<g, 256, 0, st>>>(in, emb, off, out, B, L, S, H, dx, dy_dx); break;
+        case 1: hash_forward_kernel<D, 1><<<g, 256, 0, st>>>(in, emb, off, out, B, L, ls, dx, dy_dx); break;
+        case 2: hash_forward_kernel<D, 2><<<g, 256, 0, st>>>(in, emb, off, out, B, L, ls, dx, dy_dx); break;
+        case 4: hash_forward_kernel<D, 4><<<g, 256, 0, st>>>(in, emb, off, out, B, L, ls, dx, dy_dx); break;
+        case 8: hash_forward_kernel<D, 8><<<g, 256, 0, st>>>(in, emb, off, out, B, L, ls, dx, dy_dx); break;
         default: NICER_FAIL(-1, "GridEncoding: C must be 1, 2, 4, or 8.");
     }
     return 0;
@@ -284,10 +285,11 @@ static int launch_backward(uint32_t C, dim3 g, cudaStream_t st, const float *gra
                            float *gg, uint32_t B, uint32_t L, float S, uint32_t H, bool dx, const float *dy_dx,
                            float *gin) {
     const uint32_t gb = div_up(B, 256);
+    const LevelScales ls = host_level_scales(L, S, H);
     switch (C) {
 #define CASE(CC)                                                                                       \
     case CC:                                                                                           \
-        hash_backward_kernel<D, CC><<<g, 256, 0, st>>>(grad, in, off, gg, B, L, S, H);                 \
+        hash_backward_kernel<D, CC><<<g, 256, 0, st>>>(grad, in, off, gg, B, L, ls);                 \
         if (dx) hash_input_backward_kernel<D, CC><<<gb, 256, 0, st>>>(grad, dy_dx, gin, B, L);         \
         break;
         CASE(1) CASE(2) CASE(4) CASE(8)
@@ -301,10 +303,11 @@ template <uint32_t D>
 static int launch_second(uint32_t C, dim3 g, cudaStream_t st, const float *grad, const float *in, const int *off,
                          const float *dy_dx, const float *ggx, float *gg, float *g2, uint32_t B, uint32_t L, float S,
                          uint32_t H) {
+    const LevelScales ls = host_level_scales(L, S, H);
     switch (C) {
-        case 2: hash_second_backward_kernel<D, 2><<<g, 256, 0, st>>>(grad, in, off, dy_dx, ggx, gg, g2, B, L, S, H); break;
-        case 4: hash_second_backward_kernel<D, 4><<<g, 256, 0, st>>>(grad, in, off, dy_dx, ggx, gg, g2, B, L, S, H); break;
-        case 8: hash_second_backward_kernel<D, 8><<<g, 256, 0, st>>>(grad, in, off, dy_dx, ggx, gg, g2, B, L, S, H); break;
+        case 2: hash_second_backward_kernel<D, 2><<<g, 256, 0, st>>>(grad, in, off, dy_dx, ggx, gg, g2, B, L, ls); break;
+        case 4: hash_second_backward_kernel<D, 4><<<g, 256, 0, st>>>(grad, in, off, dy_dx, ggx, gg, g2, B, L, ls); break;
+        case 8: hash_second_backward_kernel<D, 8><<<g, 256, 0, st>>>(grad, in, off, dy_dx, ggx, gg, g2, B, L, ls); break;
         default: NICER_FAIL(-1, "GridEncoding: C must be 1, 2, 4, or 8.");  // C=1 unsupported as in hashencoder.cu:708-714
     }
     return 0;

@@ -47,6 +47,17 @@ NHD float d2softplus100(float z) {
     return (1.0f - s) * s * SP_BETA;
 }
 
+// x*y rounded to fp32 and never contracted into a following subtraction (the fractional part of x*scale must
+// be taken from the ROUNDED product, as the un-fused evaluation does)
+NHD float fmul_exact(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;
+    return r;
+#endif
+}
+
 NHD float sstep(float v) { return v * v * (3.0f - 2.0f * v); }
 NHD float sstep_d(float v) { return 6.0f * v * (1.0f - v); }
 
@@ -58,11 +69,23 @@ struct LevelInfo {
     float scale;            // exp2f(level*S)*H - 1
 };
 
-NHD LevelInfo make_level(const int32_t *offsets, uint32_t level, float S, uint32_t H) {
+// Per-level scales exp2f(level*S)*H - 1 are evaluated on the HOST (common.cuh: host_level_scales) in the same fp32
+// steps as the reference (hashencoder.cu:180) and handed to the kernels by value: CUDA's exp2f (2 ulp) and glibc's
+// (correctly rounded) differ in the last bit for non-integer exponents, and one ulp of `scale` at resolution 2048
+// already moves a sample by 1e-4 of a cell.
+struct LevelScales { float s[16]; };
+
+inline LevelScales host_level_scales(uint32_t L, float S, uint32_t H) {
+    LevelScales ls;
+    for (uint32_t l = 0; l < 16; ++l) ls.s[l] = (l < L) ? exp2f((float)l * S) * (float)H - 1.0f : 0.f;
+    return ls;
+}
+
+NHD LevelInfo make_level(const int32_t *offsets, uint32_t level, float scale) {
     LevelInfo li;
     li.offset = (uint32_t)offsets[level];
     li.hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-    li.scale = exp2f((float)level * S) * (float)H - 1.0f;
+    li.scale = scale;
     li.resolution = (uint32_t)ceilf(li.scale) + 1u;
     return li;
 }
@@ -93,7 +116,7 @@ NHD Cell3 locate3(const LevelInfo &li, const float u[3]) {
     c.scale = li.scale;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        float p = u[d] * li.scale;
+        float p = fmul_exact(u[d], li.scale);
         float f = floorf(p);
         c.pg[d] = (uint32_t)f;
         p -= (float)c.pg[d];

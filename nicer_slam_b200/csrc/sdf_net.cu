@@ -36,7 +36,7 @@ static SdfSmemLayout sdf_layout(int n_hidden) {
 }
 
 // Stage the network into shared memory (transposed) and build the device view.
-__device__ void stage_sdf_net(const nicer_sdf_net_t &net, const SdfSmemLayout &lay, float *smem, SdfNetView &nv) {
+__device__ void stage_sdf_net(const nicer_sdf_net_t &net, const LevelScales &ls, const SdfSmemLayout &lay, float *smem, SdfNetView &nv) {
     const int n = (int)net.n_hidden;
     const int L = (int)net.grid.L, C = (int)net.grid.C;
     const int d_pe = 3 + 6 * (int)net.multires;
@@ -69,7 +69,7 @@ __device__ void stage_sdf_net(const nicer_sdf_net_t &net, const SdfSmemLayout &l
         }
     }
     LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
-    for (int l = tid; l < L; l += nt) lv[l] = make_level(net.grid.offsets, (uint32_t)l, net.grid.S, net.grid.H);
+    for (int l = tid; l < L; l += nt) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
     nv.W0t = W0t;
     for (int i = 0; i < 3; ++i) { nv.Wt[i] = smem + lay.Wt[i]; nv.b[i] = smem + lay.b[i]; }
     nv.WLt = smem + lay.WLt;
@@ -85,11 +85,11 @@ __device__ void stage_sdf_net(const nicer_sdf_net_t &net, const SdfSmemLayout &l
 
 template <int C>
 __global__ void __launch_bounds__(SDF_BLOCK, 2)
-sdf_forward_kernel(const nicer_sdf_net_t net, const SdfSmemLayout lay, const float *__restrict__ X, uint32_t P,
+sdf_forward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSmemLayout lay, const float *__restrict__ X, uint32_t P,
                    uint32_t flags, float *sdf, float *feat_fm, float *grad, float *Z, float *R, float *DYDX) {
     extern __shared__ __align__(16) float smem[];
     SdfNetView nv;
-    stage_sdf_net(net, lay, smem, nv);
+    stage_sdf_net(net, ls, lay, smem, nv);
     __syncthreads();
     float *col = smem + lay.col + threadIdx.x;
     const uint32_t tiles = (P + SDF_BLOCK - 1) / SDF_BLOCK;
@@ -101,13 +101,13 @@ sdf_forward_kernel(const nicer_sdf_net_t net, const SdfSmemLayout lay, const flo
 
 template <int C>
 __global__ void __launch_bounds__(SDF_BLOCK, 2)
-sdf_backward_kernel(const nicer_sdf_net_t net, const SdfSmemLayout lay, const float *__restrict__ X, uint32_t P,
+sdf_backward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSmemLayout lay, const float *__restrict__ X, uint32_t P,
                     const float *Z, const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
                     const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB, float *AB,
                     float *TAN, float *H0, float *T0) {
     extern __shared__ __align__(16) float smem[];
     SdfNetView nv;
-    stage_sdf_net(net, lay, smem, nv);
+    stage_sdf_net(net, ls, lay, smem, nv);
     __syncthreads();
     float *col = smem + lay.col + threadIdx.x;
     const uint32_t tiles = (P + SDF_BLOCK - 1) / SDF_BLOCK;
@@ -158,6 +158,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
     }
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_forward: n_hidden > 3 not built");
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);
     const uint32_t tiles = div_up(P, SDF_BLOCK);
     const uint32_t grid = tiles < (uint32_t)(2 * num_sms()) ? tiles : (uint32_t)(2 * num_sms());
@@ -165,7 +166,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
 #define LAUNCH(CC)                                                                                            \
     do {                                                                                                      \
         if (int e = prep_kernel(sdf_forward_kernel<CC>, smem, "nicer_sdf_forward")) return e;                 \
-        sdf_forward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, lay, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX); \
+        sdf_forward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, ls, lay, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX); \
     } while (0)
     switch (net->grid.C) {
         case 2: LAUNCH(2); break;
@@ -188,6 +189,7 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
     if (net->n_hidden > 1 && !R) NICER_FAIL(-1, "nicer_sdf_backward: R required for n_hidden > 1");
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_backward: n_hidden > 3 not built");
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);
     const uint32_t tiles = div_up(P, SDF_BLOCK);
     const uint32_t grid = tiles < (uint32_t)(2 * num_sms()) ? tiles : (uint32_t)(2 * num_sms());
@@ -195,7 +197,7 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
 #define LAUNCH(CC)                                                                                              \
     do {                                                                                                        \
         if (int e = prep_kernel(sdf_backward_kernel<CC>, smem, "nicer_sdf_backward")) return e;                 \
-        sdf_backward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, lay, x, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, \
+        sdf_backward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, ls, lay, x, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, \
                                                                grad_x, grad_table, ZB, QB, AB, TAN, H0, T0);    \
     } while (0)
     switch (net->grid.C) {

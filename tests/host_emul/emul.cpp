@@ -40,7 +40,7 @@ struct HostSdf {
         WLt.assign(NICER_W * NICER_W, 0.f); wl_sdf.assign(NICER_W, 0.f); b0.assign(NICER_W, 0.f); bl_feat.assign(NICER_W, 0.f);
         for (int j = 0; j < nfeat; ++j) for (int k = 0; k < NICER_W; ++k) WLt[k * NICER_W + j] = net.W[n][(1 + j) * NICER_W + k];
         for (int i = 0; i < NICER_W; ++i) { wl_sdf[i] = net.W[n][i]; b0[i] = net.b[0][i]; if (i < nfeat) bl_feat[i] = net.b[n][1 + i]; }
-        for (int l = 0; l < L; ++l) lv.push_back(make_level(net.grid.offsets, l, net.grid.S, net.grid.H));
+        for (int l = 0; l < L; ++l) lv.push_back(make_level(net.grid.offsets, l, host_level_scales(net.grid.L, net.grid.S, net.grid.H).s[l]));
         nv.W0t = W0t.data();
         for (int i = 0; i < 3; ++i) { nv.Wt[i] = Wt[i].data(); nv.b[i] = b[i].data(); }
         nv.WLt = WLt.data(); nv.wl_sdf = wl_sdf.data(); nv.b0 = b0.data(); nv.bl_feat = bl_feat.data();
@@ -65,7 +65,7 @@ struct HostColor {
             for (int j = 0; j < NICER_W; ++j) { b[l - 1][j] = net.b[l][j]; for (int k = 0; k < NICER_W; ++k) Wt[l - 1][k * NICER_W + j] = net.W[l][j * NICER_W + k]; }
         }
         WL.assign(net.W[n], net.W[n] + 3 * NICER_W); b0.assign(net.b[0], net.b[0] + NICER_W);
-        for (int l = 0; l < L; ++l) lv.push_back(make_level(net.grid.offsets, l, net.grid.S, net.grid.H));
+        for (int l = 0; l < L; ++l) lv.push_back(make_level(net.grid.offsets, l, host_level_scales(net.grid.L, net.grid.S, net.grid.H).s[l]));
         nv.W0t = W0t.data();
         for (int i = 0; i < 3; ++i) { nv.Wt[i] = Wt[i].data(); nv.b[i] = b[i].data(); }
         nv.WL = WL.data(); nv.b0 = b0.data();
@@ -232,7 +232,7 @@ template <int C>
 static void hash_fwd(const float *in, const float *emb, const int32_t *off, float *out, uint32_t B, uint32_t L, float S,
                      uint32_t H, int dx, float *dy_dx) {
     for (uint32_t l = 0; l < L; ++l) {
-        const LevelInfo li = make_level(off, l, S, H);
+        const LevelInfo li = make_level(off, l, host_level_scales(L, S, H).s[l]);
         for (uint32_t b = 0; b < B; ++b) {
             float feat[C], df[3][C];
             if (dx) encode_level<C, true>(emb, li, in + 3 * (size_t)b, feat, df);
@@ -247,7 +247,7 @@ template <int C>
 static void hash_bwd(const float *grad, const float *in, const int32_t *off, float *gg, uint32_t B, uint32_t L, float S,
                      uint32_t H, const float *ggx /* NULL: first order */) {
     for (uint32_t l = 0; l < L; ++l) {
-        const LevelInfo li = make_level(off, l, S, H);
+        const LevelInfo li = make_level(off, l, host_level_scales(L, S, H).s[l]);
         for (uint32_t b = 0; b < B; ++b) {
             Cell3 cell = locate3(li, in + 3 * (size_t)b);
             if (!cell.inside) continue;

@@ -89,7 +89,7 @@ def test_color_net_16_levels(stage):
     tab = net["table"].detach().to(dev).requires_grad_(True)
     vgb = [[t.detach().to(dev).requires_grad_(True) for t in l] for l in net["layers"]]
     rgb2 = ops.ColorNetFn.apply(*ins2, tab, spec.offsets.to(dev), meta, *_wb(vgb))
-    assert rel(rgb2, rgb) < 1e-5
+    assert rel(rgb2, rgb) < 1e-4   # level 15 (res 2048): one fp32 ulp of x*scale is 1e-4 of a cell
     got = torch.autograd.grad((rgb2 * wR.to(dev)).sum(), ins2 + [tab] + [t for l in vgb for t in l], allow_unused=True)
     for a, b in zip(got, want):
         if b is None:
