@@ -35,6 +35,9 @@ extern "C" {
 
 const char *nicer_last_error(void);
 int nicer_version(void);
+/* 1 (default): the sdf-only pass runs on the tcgen05 (3xTF32) kernel; 0: fp32 SIMT kernel (A/B testing).
+ * Also controlled by the environment variable NICER_DISABLE_TC=1. */
+int nicer_set_tensor_cores(int enabled);
 
 /* ---------------------------------------------------------------------------------------------
  * Drop-in native op of hashencoder/ (same argument meaning and layouts as hashencoder.h:13-15).

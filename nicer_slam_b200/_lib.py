@@ -47,6 +47,7 @@ _SIGS = {
     "nicer_composite_backward": [_fp] * 6 + [_u32, _u32, _u32] + [_fp] * 11,
     "nicer_sampler_weights": [_fp] * 4 + [_u32, _u32, _u32, _fp, _fp],
     "nicer_voxel_count": [_fp, _u32, _fp, _u32, _fp],
+    "nicer_set_tensor_cores": [C.c_int],
 }
 
 _handle = None

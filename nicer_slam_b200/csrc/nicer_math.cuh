@@ -30,22 +30,71 @@ namespace nicer {
 constexpr float SP_BETA = 100.0f;
 constexpr float SP_THRESH = 20.0f;
 
-NHD float softplus100(float z) {
+// Device fast path: one exp shared by softplus / sigmoid / sigmoid', built from ex2.approx + lg2.approx + rcp.approx
+// with the argument-reduction error of exp and the rounding error of 1+e compensated, so that the result is fp32-faithful
+// (|error| <~ 2e-7 relative on e, <~ 3e-9 absolute on softplus) at ~25 instructions instead of ~75 for libm's
+// expf + log1pf + IEEE division.  The host build (tests/host_emul) keeps libm.
+struct SpEval { float a, s1, s2; };   // softplus(z), softplus'(z), softplus''(z)
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exp(t) for t <= 20
+__device__ __forceinline__ float exp_fast(float t) {
+    const float L2E = 1.4426950408889634f, L2E_LO = 1.925963033500803e-8f, LN2 = 0.6931471805599453f;
+    const float y = t * L2E;
+    const float r = fmaf(t, L2E, -y) + t * L2E_LO;      // t*log2(e) - y, to ~2^-48
+    const float e = ex2_approx(y);
+    return fmaf(e, r * LN2, e);
+}
+// log(1+e), e >= 0, given u = 1+e (rounded)
+__device__ __forceinline__ float log1p_fast(float e, float u, float ru) {
+    const float LN2 = 0.6931471805599453f;
+    if (e < 0.0078125f) return e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.0f);
+    const float l = lg2_approx(u) * LN2;
+    return l - ((u - 1.0f) - e) * ru;                   // first-order correction for the rounding of 1+e
+}
+__device__ __forceinline__ SpEval sp_eval(float z) {
+    SpEval r;
+    const float t = z * SP_BETA;
+    if (t > SP_THRESH) { r.a = z; r.s1 = 1.0f; r.s2 = 0.0f; return r; }
+    const float e = exp_fast(t);
+    const float u = 1.0f + e;
+    const float ru = rcp_approx(u);
+    r.a = log1p_fast(e, u, ru) * 0.01f;
+    r.s1 = e * ru;
+    r.s2 = (t < SP_THRESH) ? (1.0f - r.s1) * r.s1 * SP_BETA : 0.0f;
+    return r;
+}
+__device__ __forceinline__ float softplus100(float z) { return sp_eval(z).a; }
+__device__ __forceinline__ float dsoftplus100(float z) {
+    const float t = z * SP_BETA;
+    if (t > SP_THRESH) return 1.0f;
+    const float e = exp_fast(t);
+    return e * rcp_approx(1.0f + e);
+}
+__device__ __forceinline__ float d2softplus100(float z) { return sp_eval(z).s2; }
+#else
+inline float softplus100(float z) {
     float t = z * SP_BETA;
     return t > SP_THRESH ? z : log1pf(expf(t)) / SP_BETA;
 }
-NHD float dsoftplus100(float z) {
+inline float dsoftplus100(float z) {
     float t = z * SP_BETA;
     if (t > SP_THRESH) return 1.0f;
     float e = expf(t);
     return e / (e + 1.0f);
 }
-NHD float d2softplus100(float z) {
+inline float d2softplus100(float z) {
     float t = z * SP_BETA;
     if (!(t < SP_THRESH)) return 0.0f;
     float s = 1.0f / (1.0f + expf(-t));
     return (1.0f - s) * s * SP_BETA;
 }
+inline SpEval sp_eval(float z) { SpEval r = {softplus100(z), dsoftplus100(z), d2softplus100(z)}; return r; }
+#endif
 
 // x*y rounded to fp32 and never contracted into a following subtraction (the fractional part of x*scale must
 // be taken from the ROUNDED product, as the un-fused evaluation does)
@@ -90,15 +139,24 @@ NHD LevelInfo make_level(const int32_t *offsets, uint32_t level, float scale) {
     return li;
 }
 
-// entry index (not multiplied by C) of grid vertex p within a level
-NHD uint32_t vertex_index3(const LevelInfo &li, uint32_t px, uint32_t py, uint32_t pz) {
-    uint32_t stride = 1, index = 0;
+// The reference's index rule (hashencoder.cu:54-73) accumulates p[d]*stride with stride *= resolution while
+// stride <= hashmap_size (uint32 arithmetic, wraps) and switches to the XOR hash when the final stride exceeds the level
+// size; which of the two happens depends on the level only, so it is decided once per level.
+NHD bool level_is_dense(const LevelInfo &li) {
+    uint32_t stride = 1;
     const uint32_t hs = li.hashmap_size, res = li.resolution;
-    if (stride <= hs) { index += px * stride; stride *= res; }
-    if (stride <= hs) { index += py * stride; stride *= res; }
-    if (stride <= hs) { index += pz * stride; stride *= res; }
-    if (stride > hs) index = (px * 1u) ^ (py * 2654435761u) ^ (pz * 805459861u);
-    return index % hs;
+    if (stride <= hs) stride *= res;
+    if (stride <= hs) stride *= res;
+    if (stride <= hs) stride *= res;
+    return !(stride > hs);
+}
+
+// entry index (not multiplied by C) of grid vertex p within a level
+NHD uint32_t vertex_index3(const LevelInfo &li, bool dense, uint32_t px, uint32_t py, uint32_t pz) {
+    const uint32_t hs = li.hashmap_size, res = li.resolution;
+    uint32_t index = dense ? px + res * (py + res * pz) : ((px * 1u) ^ (py * 2654435761u) ^ (pz * 805459861u));
+    if ((hs & (hs - 1u)) == 0u) return index & (hs - 1u);
+    return index >= hs ? index % hs : index;
 }
 
 // Interpolation cell of a point u in [0,1]^3 at one level.
@@ -127,9 +185,10 @@ NHD Cell3 locate3(const LevelInfo &li, const float u[3]) {
 }
 
 NHD void corner_indices(const LevelInfo &li, const Cell3 &c, uint32_t idx[8]) {
+    const bool dense = level_is_dense(li);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-        idx[k] = vertex_index3(li, c.pg[0] + (k & 1), c.pg[1] + ((k >> 1) & 1), c.pg[2] + ((k >> 2) & 1));
+        idx[k] = vertex_index3(li, dense, c.pg[0] + (k & 1), c.pg[1] + ((k >> 1) & 1), c.pg[2] + ((k >> 2) & 1));
 }
 
 // trilinear weights in the reference's corner order (bit d of k selects the upper vertex in dim d)

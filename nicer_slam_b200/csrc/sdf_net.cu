@@ -135,6 +135,9 @@ static int check_sdf_net(const nicer_sdf_net_t *net, const char *who) {
     return 0;
 }
 
+bool tc_enabled();
+int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, cudaStream_t st);
+
 template <typename K>
 static int prep_kernel(K kernel, size_t smem_bytes, const char *who) {
     NICER_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes), who);
@@ -157,6 +160,9 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
         if (!(flags & NICER_SDF_NO_FEAT) && !feat_fm) NICER_FAIL(-1, "nicer_sdf_forward: feat_fm is NULL");
     }
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_forward: n_hidden > 3 not built");
+    // tensor-core (tcgen05, 3xTF32) path for the sdf-only pass; multires 6 + 64-wide layers is what it is built for
+    if (sdf_only && tc_enabled() && net->multires == 6)
+        return launch_sdf_only_tc(net, x, P, flags, sdf, (cudaStream_t)stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);

@@ -252,11 +252,12 @@ NHD void sdf_backward_sample(const SdfNetView &nv, const float *X, uint32_t p, u
             const size_t o = ((size_t)(l - 1) * NICER_W + j) * Ps + p;
             const float z = Z[o];
             const float r = (l < n) ? R[o] : nv.wl_sdf[j];
-            const float s1 = dsoftplus100(z), s2 = d2softplus100(z);
+            const SpEval sp = sp_eval(z);
+            const float s1 = sp.s1, s2 = sp.s2;
             const float tan = acc[j] * s1;
             TAN[o] = tan;
             QB[o] = r * s1;
-            AB[o] = softplus100(z);
+            AB[o] = sp.a;
             ZB[o] = acc[j] * r * s2;
             col[j * cs] = tan;
         }

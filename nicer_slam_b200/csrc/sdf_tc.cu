@@ -1,0 +1,226 @@
+// Tensor-core (tcgen05, sm_100a) SDF-only forward: the sampler's 640-samples-per-ray pass and get_sdf_vals
+// (/root/reference/code/model/ray_sampler.py:100-102, model/base_networks.py:27-32,223-228).
+//
+// One CTA = 128 threads = 128 points = the 128 TMEM lanes of one accumulator tile.  Per point, one thread builds the
+// network input (x, NeRF PE, hash/dense grid features) in registers and writes it with tcgen05.st into TMEM as the
+// A operand (hi and lo halves of the 3xTF32 split); thread 0 issues tcgen05.mma kind::tf32 (M=128, N=64, K=8 per
+// instruction; 3 MMAs per K-step for fp32 fidelity) against the weights held in shared memory in the UMMA K-major
+// no-swizzle layout; every thread then reads its own accumulator row with tcgen05.ld.32x32b, applies bias +
+// Softplus(100) and writes the next layer's A operand.  The last layer (one output: the sdf) is a 64-term fp32 dot.
+#include "common.cuh"
+#include "sdf_sample.cuh"
+#include "tc_common.cuh"
+
+namespace nicer {
+
+constexpr int TC_BLOCK = 128;
+constexpr int TC_K0 = 72;                 // layer-0 K padded to a multiple of 8 (d_in <= 71)
+constexpr int TC_COL_AHI = 0;             // TMEM columns: A hi [0,72), A lo [72,144), D [144,208)
+constexpr int TC_COL_ALO = TC_K0;
+constexpr int TC_COL_D = 2 * TC_K0;
+constexpr int TC_TMEM_COLS = 256;
+
+struct TcSmemLayout {
+    int w_hi[4], w_lo[4];   // per MMA layer: [K/4][64][4] floats (K-major core-matrix layout)
+    int bias[4];            // per MMA layer bias [64]
+    int wl_sdf, lv, total_floats;
+};
+
+static TcSmemLayout tc_layout(int n_hidden) {
+    TcSmemLayout s;
+    int o = 0;
+    for (int l = 0; l < 4; ++l) {
+        const int K = (l == 0) ? TC_K0 : NICER_W;
+        s.w_hi[l] = o; if (l < n_hidden) o += K * NICER_W;
+        s.w_lo[l] = o; if (l < n_hidden) o += K * NICER_W;
+        s.bias[l] = o; if (l < n_hidden) o += NICER_W;
+    }
+    s.wl_sdf = o; o += NICER_W;
+    s.lv = o; o += NICER_MAX_LEVELS * 4;
+    s.total_floats = o;
+    return s;
+}
+
+// stage W [64 out][K_src in] (row-major, global) as hi/lo in the UMMA K-major no-swizzle layout:
+// element (n, k) -> chunk c = k/4 : base[(c*64 + n)*4 + k%4]; rows k >= K_src are zero padding
+__device__ void tc_stage_weight(const float *__restrict__ W, int K_src, int K_pad, float *hi, float *lo) {
+    for (int i = threadIdx.x; i < K_pad * NICER_W; i += blockDim.x) {
+        const int n = i / K_pad, k = i - n * K_pad;
+        const float w = (k < K_src) ? W[(size_t)n * K_src + k] : 0.f;
+        const float h = tc::tf32_hi(w);
+        const int dst = ((k >> 2) * NICER_W + n) * 4 + (k & 3);
+        hi[dst] = h;
+        lo[dst] = w - h;
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(TC_BLOCK, 2)
+sdf_only_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcSmemLayout lay, const float *__restrict__ X,
+                   uint32_t P, uint32_t accumulate, float *__restrict__ sdf) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int n = (int)net.n_hidden;
+    const int L = (int)net.grid.L;
+    const int d_pe = 3 + 6 * (int)net.multires;
+    const int d_in = d_pe + L * C;
+
+    // ---- one-time setup: weights (hi/lo), biases, level table, mbarrier, TMEM
+    for (int l = 0; l < n; ++l) {
+        tc_stage_weight(net.W[l], l == 0 ? d_in : NICER_W, l == 0 ? TC_K0 : NICER_W, smem + lay.w_hi[l], smem + lay.w_lo[l]);
+        for (int i = tid; i < NICER_W; i += TC_BLOCK) smem[lay.bias[l] + i] = net.b[l][i];
+    }
+    for (int i = tid; i < NICER_W; i += TC_BLOCK) smem[lay.wl_sdf + i] = net.W[n][i];
+    LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
+    for (int l = tid; l < L; l += TC_BLOCK) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    if (tid == 0) { tc::mbar_init(&mma_bar, 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_slot, TC_TMEM_COLS);
+    // make the generic-proxy weight writes visible to the tensor core (async proxy) before any MMA
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    const float bl_sdf = net.b[n][0];
+    const float df = net.grid.divide_factor;
+    constexpr uint32_t IDESC = tc::idesc_tf32(128, NICER_W);
+    uint32_t parity = 0;
+
+    const uint32_t tiles = (P + TC_BLOCK - 1) / TC_BLOCK;
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        uint32_t p = t * TC_BLOCK + tid;
+        const bool valid = p < P;
+        if (!valid) p = P - 1;   // keep every warp converged for the .sync.aligned TMEM ops
+        // ---------------- network input -> TMEM (A operand of layer 0)
+        {
+            const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+            float h0[TC_K0];
+            h0[0] = x[0]; h0[1] = x[1]; h0[2] = x[2];
+            {
+                float fr = 1.0f;
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    if (f < (int)net.multires) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            float s, c;
+                            sincosf(x[d] * fr, &s, &c);
+                            h0[3 + 6 * f + d] = s;
+                            h0[3 + 6 * f + 3 + d] = c;
+                        }
+                    }
+                    fr *= 2.0f;
+                }
+            }
+            float u[3];
+            to_unit(x, df, u);
+#pragma unroll
+            for (int k = 39; k < TC_K0; ++k) h0[k] = 0.f;
+            if (d_pe == 39) {
+#pragma unroll
+                for (int l = 0; l < 32 / C; ++l) {
+                    if (l < L) {
+                        float feat[C], dummy[3][C];
+                        encode_level<C, false>(net.grid.table, lv[l], u, feat, dummy);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) h0[39 + l * C + c] = feat[c];
+                    }
+                }
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < TC_K0 / 8; ++c8)
+                tc::tmem_st8_split(lane_base + TC_COL_AHI + c8 * 8, lane_base + TC_COL_ALO + c8 * 8, &h0[c8 * 8]);
+        }
+        float a[NICER_W];
+        for (int l = 0; l < n; ++l) {
+            const int K = (l == 0) ? TC_K0 : NICER_W;
+            tc::wait_st();
+            tc::fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after_sync();
+                const uint32_t whi = tc::smem_u32(smem + lay.w_hi[l]), wlo = tc::smem_u32(smem + lay.w_lo[l]);
+                for (int ks = 0; ks < K / 8; ++ks) {
+                    // one K-step = 8 tf32 = 2 chunks of 16 B; chunk stride (LBO) = 64 rows * 16 B, 8-row group stride (SBO) = 128 B
+                    const uint64_t bhi = tc::smem_desc(whi + (uint32_t)ks * 2u * 1024u, 1024u, 128u);
+                    const uint64_t blo = tc::smem_desc(wlo + (uint32_t)ks * 2u * 1024u, 1024u, 128u);
+                    const uint32_t ahi = tmem_base + TC_COL_AHI + ks * 8, alo = tmem_base + TC_COL_ALO + ks * 8;
+                    tc::mma_tf32_ts(tmem_base + TC_COL_D, ahi, bhi, IDESC, ks > 0 ? 1u : 0u);
+                    tc::mma_tf32_ts(tmem_base + TC_COL_D, alo, bhi, IDESC, 1u);
+                    tc::mma_tf32_ts(tmem_base + TC_COL_D, ahi, blo, IDESC, 1u);
+                }
+                tc::mma_commit(&mma_bar);
+            }
+            tc::mbar_wait(&mma_bar, parity);
+            parity ^= 1u;
+            __syncwarp();
+            tc::fence_after_sync();
+#pragma unroll
+            for (int c8 = 0; c8 < NICER_W / 8; ++c8) tc::tmem_ld8(lane_base + TC_COL_D + c8 * 8, &a[c8 * 8]);
+            tc::wait_ld();
+            const float *bias = smem + lay.bias[l];
+#pragma unroll
+            for (int j = 0; j < NICER_W; ++j) a[j] = softplus100(a[j] + bias[j]);
+            if (l + 1 < n) {
+#pragma unroll
+                for (int c8 = 0; c8 < NICER_W / 8; ++c8)
+                    tc::tmem_st8_split(lane_base + TC_COL_AHI + c8 * 8, lane_base + TC_COL_ALO + c8 * 8, &a[c8 * 8]);
+            }
+        }
+        // ---------------- output layer: sdf only
+        float s = bl_sdf;
+        const float *wl = smem + lay.wl_sdf;
+#pragma unroll
+        for (int k = 0; k < NICER_W; ++k) s += wl[k] * a[k];
+        if (valid) {
+            if (accumulate) sdf[p] += s; else sdf[p] = s;
+        }
+        // the next tile's tcgen05.st may not overtake this tile's tcgen05.ld of D (ordered by wait_ld above)
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+static int g_tc_enabled = -1;
+bool tc_enabled() {
+    if (g_tc_enabled < 0) {
+        const char *e = getenv("NICER_DISABLE_TC");
+        g_tc_enabled = (e && e[0] == '1') ? 0 : 1;
+    }
+    return g_tc_enabled == 1;
+}
+void set_tc_enabled(int on) { g_tc_enabled = on ? 1 : 0; }
+
+int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, cudaStream_t st) {
+    TcSmemLayout lay = tc_layout((int)net->n_hidden);
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
+    const size_t smem = (size_t)lay.total_floats * sizeof(float);
+    const uint32_t tiles = div_up(P, TC_BLOCK);
+    const uint32_t grid = tiles < (uint32_t)(2 * num_sms()) ? tiles : (uint32_t)(2 * num_sms());
+    const uint32_t acc = (flags & NICER_SDF_ACCUMULATE) ? 1u : 0u;
+#define LAUNCH(CC)                                                                                                  \
+    do {                                                                                                            \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_only_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
+                   "nicer_sdf_forward(tc)");                                                                        \
+        sdf_only_tc_kernel<CC><<<grid, TC_BLOCK, smem, st>>>(*net, ls, lay, x, P, acc, sdf);                        \
+    } while (0)
+    switch (net->grid.C) {
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        default: LAUNCH(8); break;
+    }
+#undef LAUNCH
+    NICER_CHECK_LAUNCH("nicer_sdf_forward(tc)");
+    return 0;
+}
+
+}  // namespace nicer
+
+extern "C" int nicer_set_tensor_cores(int enabled) {
+    nicer::set_tc_enabled(enabled);
+    return 0;
+}

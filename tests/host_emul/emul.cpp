@@ -21,6 +21,7 @@ static int fail(const char *fmt, ...) {
 }
 extern "C" const char *nicer_last_error(void) { return g_err; }
 extern "C" int nicer_version(void) { return -1; }   // negative: emulation
+extern "C" int nicer_set_tensor_cores(int) { return 0; }
 
 namespace {
 struct HostSdf {
