@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import ops
+from .. import ops, parallel
 from ..utils import rend_util
 from ..utils.general import uv2patch
 from .base_networks import ImplicitNetworkGrid_COMBINE, RenderingNetwork
@@ -59,6 +59,7 @@ class SLAMNetwork(nn.Module):
         self.register_buffer("voxels", torch.zeros(self.voxel_res, self.voxel_res, self.voxel_res), persistent=False)
         self.voxels_shape = self.voxels.shape
         self.rng = DeviceRng()
+        self.ray_parallel = True   # under torch.distributed: rays are sharded over ranks (parallel.py)
         self._sync_density_voxels()
 
     def _sync_density_voxels(self):
@@ -70,7 +71,15 @@ class SLAMNetwork(nn.Module):
         """Histogram the main-pass points into the 64^3 counter (network.py:62-76), in place."""
         if not self.voxels.is_contiguous():
             self.voxels = self.voxels.contiguous()
-        ops.voxel_count(x, self.voxels)
+        if self.ray_parallel and parallel.world() > 1:
+            # ray-parallel ranks each count their own share of the points: sum the increments so that the density of
+            # THIS forward (and every replica of the counter) sees all of them, as the single-process reference does
+            delta = torch.zeros_like(self.voxels)
+            ops.voxel_count(x, delta)
+            parallel.all_reduce_sum_(delta)
+            self.voxels += delta
+        else:
+            ops.voxel_count(x, self.voxels)
         self._sync_density_voxels()
 
     # ------------------------------------------------------------------------------------------------

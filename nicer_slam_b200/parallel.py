@@ -114,10 +114,7 @@ def allreduce_gradients(model, extra=(), average=False):
         off += n
 
 
-def allreduce_voxels(model, before):
-    """Sum the voxel-counter *increments* of all ranks (SLAMNetwork.update_voxels is per-rank on sharded rays)."""
-    if world() == 1:
-        return
-    delta = model.voxels - before
-    dist.all_reduce(delta, op=dist.ReduceOp.SUM)
-    model.voxels.copy_(before + delta)
+def all_reduce_sum_(t):
+    if world() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
