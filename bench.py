@@ -297,6 +297,7 @@ def main():
     ap.add_argument("--color-logmap", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -333,13 +334,41 @@ def main():
     P = args.rays * S_MAIN
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)   # 192 MiB > 126 MB L2
 
+    graphed = None
+    if not args.no_graph:
+        from nicer_slam_b200.graph import GraphedStep
+        graphed = GraphedStep(lambda: step.run(), warmup=3)     # forward + loss + backward as ONE CUDA graph
+
     def one(e2e=False):
         flush.add_(1.0)                                         # L2 flush between timed iterations
-        v = step.run_e2e() if e2e else step.run()
+        if graphed is not None:
+            if e2e:   # pinned host -> static device buffers, replay, loss back to the host
+                for k, v in step.pinned.items():
+                    (step.cam7.data if k == "cam7" else step.dev[k]).copy_(v, non_blocking=True)
+            loss = graphed.replay()
+            v = float(loss.item()) if e2e else loss
+        else:
+            v = step.run_e2e() if e2e else step.run()
         if world > 1:
             parallel.allreduce_gradients(step.model, extra=[step.cam7])
         return v
 
+    # launches of our kernels per step (counted on an eager step; a graph replay launches the same kernels)
+    _lib.launch_count = 0
+    step.run()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count
+    eager_ms = None
+    if graphed is not None and rank == 0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            step.run()
+        e0.record()
+        for _ in range(5):
+            step.run()
+        e1.record()
+        torch.cuda.synchronize()
+        eager_ms = e0.elapsed_time(e1) / 5
     for _ in range(max(args.warmup, 3)):
         one()
     torch.cuda.synchronize()
@@ -396,7 +425,9 @@ def main():
                 "config": {"workload": workload, "rays_per_gpu": args.rays, "ray_samples_per_step_per_gpu": P,
                            "color_grid_log2_entries": args.color_logmap, "parallelism": f"ray-parallel x{world}",
                            "l2": "192 MiB flush buffer written between timed iterations; color grid (1 GB) > L2"},
-                "clocks": clk.summary(), "gpu_launches": launches,
+                "clocks": clk.summary(), "gpu_launches": launches if graphed is None else launches_per_step * args.steps,
+                "execution": "eager" if graphed is None else "cuda-graph replay of forward+loss+backward (eager ms/step reported as eager_ms_per_step)",
+                "eager_ms_per_step": eager_ms,
                 "e2e": {"value": e2e_val, "unit": "ray-samples/s", "h2d_bytes_per_step": step.h2d_bytes(), "d2h_bytes_per_step": 4,
                         "note": "frames (full_rgb/full_depth) are a device-resident cache; per-step uv/pose/K/sampled GT come from pinned host memory"}}
         line.update(extra)

@@ -129,7 +129,7 @@ class SLAMNetwork(nn.Module):
         output = {}
         if "edges" in ground_truth:   # optical-flow projection i -> j (network.py:153-165)
             idii, idjj, _, _ = ground_truth["edges"]
-            w2c = torch.linalg.inv(pose[idjj])
+            w2c = torch.linalg.inv_ex(pose[idjj])[0]     # inv_ex: no host-side error check (CUDA-graph safe)
             cam_pts = w2c[:, :3, :3] @ surf[idii] + w2c[:, :3, 3:]
             proj = (intrinsics[idjj][:, :3, :3] @ cam_pts).permute(0, 2, 1)
             output["flow"] = proj[..., :2] / (proj[..., 2:] + 1e-8) - uv[idii]
@@ -179,7 +179,7 @@ class SLAMNetwork(nn.Module):
         full_rgb = ground_truth["full_rgb"].reshape(bs, H, W, 3)
         full_depth = ground_truth["full_depth"].reshape(bs, H, W, 1)
         depth = rendered_depth.reshape(bs, -1, 1, 1)
-        w2c = torch.linalg.inv(pose)
+        w2c = torch.linalg.inv_ex(pose)[0]
         K3 = intrinsics[:, :3, :3]
         out = {}
         for ps in self.patchsizes:

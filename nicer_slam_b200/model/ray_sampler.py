@@ -17,7 +17,8 @@ class DeviceRng:
         return torch.rand(shape, device=device)
 
     def perm(self, n, k, device):
-        return torch.randperm(n, device=device)[:k]
+        # k distinct indices, uniformly at random (argtop-k of iid uniforms: CUDA-graph capturable, unlike randperm)
+        return torch.rand(n, device=device).topk(k).indices
 
     def eik_index(self, high, n, device):
         return torch.randint(high, (n,), device=device)
