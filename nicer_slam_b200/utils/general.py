@@ -35,7 +35,8 @@ def get_camera_from_tensor(inputs):
         inputs = inputs.unsqueeze(0)
     R = quad2rotation(inputs[:, :4])
     RT = torch.cat([R, inputs[:, 4:, None]], 2)
-    bottom = torch.tensor([0.0, 0.0, 0.0, 1.0], device=RT.device, dtype=RT.dtype).expand(RT.shape[0], 1, 4)
+    bottom = torch.zeros(RT.shape[0], 1, 4, device=RT.device, dtype=RT.dtype)   # built on the device: no H2D copy,
+    bottom[:, :, 3] = 1.0                                                         # so the step stays CUDA-graph capturable
     RT = torch.cat([RT, bottom], 1)
     return RT[0] if single else RT
 
