@@ -114,10 +114,22 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# Weight / bias gradients are plain [M,P]x[P,N] fp32 GEMMs over the sample dimension.  For large P they go to cuBLAS
+# (a library GEMM, exactly what the reference's autograd calls); nicer_outer_accum is the in-house split-K kernel used
+# for small P, on the host-emulated path and when NICER_WGRAD=native.
+import os as _os
+_WGRAD_LIBRARY_MIN_P = 0 if _os.environ.get("NICER_WGRAD", "") == "cublas" else (1 << 62 if _os.environ.get("NICER_WGRAD", "") == "native" else 16384)
+
+
 def outer_accum(A, B, Cmat, bias=None):
     """Cmat[M,N] += A[M,P] @ B[N,P]^T ; bias[M] += A.sum(1).  A, B feature-major (row stride = P)."""
     M, P = A.shape
     N = B.shape[0]
+    if A.is_cuda and P >= _WGRAD_LIBRARY_MIN_P:
+        Cmat.addmm_(A, B.t())
+        if bias is not None:
+            bias.add_(A.sum(dim=1))
+        return
     check(lib().nicer_outer_accum(ptr(A), A.stride(0), M, ptr(B), B.stride(0), N, P, ptr(Cmat), Cmat.stride(0),
                                   ptr(bias) if bias is not None else None, stream()), "nicer_outer_accum")
 
