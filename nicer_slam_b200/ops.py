@@ -114,11 +114,12 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-# Weight / bias gradients are plain [M,P]x[P,N] fp32 GEMMs over the sample dimension.  For large P they go to cuBLAS
-# (a library GEMM, exactly what the reference's autograd calls); nicer_outer_accum is the in-house split-K kernel used
-# for small P, on the host-emulated path and when NICER_WGRAD=native.
+# Weight / bias gradients are plain [M,P]x[P,N] fp32 GEMMs over the sample dimension (what the reference's autograd
+# hands to cuBLAS); nicer_outer_accum is the in-house split-K kernel.
 import os as _os
-_WGRAD_LIBRARY_MIN_P = 0 if _os.environ.get("NICER_WGRAD", "") == "cublas" else (1 << 62 if _os.environ.get("NICER_WGRAD", "") == "native" else 16384)
+# measured on B200 (demo_2 mapping step): cuBLAS sgemm is ~2x slower than nicer_outer_accum on these M=64, K=4e5
+# shapes, so the in-house kernel is the default; NICER_WGRAD=cublas switches for comparison
+_WGRAD_LIBRARY_MIN_P = 0 if _os.environ.get("NICER_WGRAD", "") == "cublas" else (1 << 62)
 
 
 def outer_accum(A, B, Cmat, bias=None):
