@@ -137,6 +137,8 @@ static int check_sdf_net(const nicer_sdf_net_t *net, const char *who) {
 
 bool tc_enabled();
 int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, cudaStream_t st);
+int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
+                          float *grad, float *Z, float *R, float *DYDX, cudaStream_t st);
 
 template <typename K>
 static int prep_kernel(K kernel, size_t smem_bytes, const char *who) {
@@ -163,6 +165,8 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
     // tensor-core (tcgen05, 3xTF32) path for the sdf-only pass; multires 6 + 64-wide layers is what it is built for
     if (sdf_only && tc_enabled() && net->multires == 6)
         return launch_sdf_only_tc(net, x, P, flags, sdf, (cudaStream_t)stream);
+    if (!sdf_only && tc_enabled() && net->multires == 6)
+        return launch_sdf_forward_tc(net, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX, (cudaStream_t)stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);

@@ -1,0 +1,374 @@
+// Tensor-core (tcgen05, sm_100a) SDF network, main differentiable pass: forward + analytic d sdf/dx.
+// Same math and same saved tensors (Z, R, DYDX) as the fp32 SIMT kernels of sdf_net.cu / sdf_sample.cuh; the
+// 64-wide mat-vecs of every layer, of the feature head and of the transposed (gradient) chain run as
+// tcgen05.mma kind::tf32 with the 3xTF32 split:
+//   * one thread = one point = one TMEM lane; activations / adjoints are written with tcgen05.st as the A operand
+//     (hi and lo column ranges), accumulator rows are read back with tcgen05.ld.32x32b by the same thread;
+//   * weights (hi, lo) live in shared memory once per CTA in the layout [k/4][64 rows][4]: read K-major
+//     (LBO = 1024 B, SBO = 128 B) it is W for the forward products, read MN-major (LBO = 128 B, SBO = 1024 B) the very
+//     same bytes are W^T for the gradient chain r_{l-1} = W_{l-1}^T q_l;
+//   * a CTA holds two independent 128-point tiles (256 threads) that share the weights and overlap each other's
+//     MMA and epilogue phases; tiles synchronise on named barriers and one mbarrier each.
+#include "common.cuh"
+#include "sdf_sample.cuh"
+#include "tc_common.cuh"
+
+namespace nicer {
+
+constexpr int TCF_THREADS = 256;
+constexpr int TCF_K0 = 80;          // layer-0 input columns, zero padded (d_in <= 71); multiple of 16 so it can be an N
+constexpr int TCF_AHI = 0, TCF_ALO = 80, TCF_D = 160, TCF_TILE_COLS = 256, TCF_TMEM = 512;
+constexpr uint32_t CHUNK_BYTES = NICER_W * 16;   // one 4-float K-chunk of all 64 rows
+
+struct TcfLayout {
+    int w_hi[5], w_lo[5], bias[5];   // index l < n: W_l (hidden producing); index n: feature head W_n[1:, :]
+    int wl_sdf, lv, total_floats;
+};
+
+static TcfLayout tcf_layout(int n_hidden) {
+    TcfLayout s;
+    int o = 0;
+    for (int l = 0; l < 5; ++l) {
+        const int K = (l == 0) ? TCF_K0 : NICER_W;
+        const bool used = l <= n_hidden;
+        s.w_hi[l] = o; if (used) o += K * NICER_W;
+        s.w_lo[l] = o; if (used) o += K * NICER_W;
+        s.bias[l] = o; if (used) o += NICER_W;
+    }
+    s.wl_sdf = o; o += NICER_W;
+    s.lv = o; o += NICER_MAX_LEVELS * 4;
+    s.total_floats = o;
+    return s;
+}
+
+// Column order of the layer-0 operand inside the kernel: [32 grid features | 39 PE values | zero padding] (grid
+// features first so that every level's C features start at a column that is a multiple of C).  tcf_col_src maps an
+// operand column to the column of the reference's input vector [PE 39 | grid L*C]  (-1: padding).
+__device__ __forceinline__ int tcf_col_src(int k, int d_in) {
+    if (k < 32) return (39 + k < d_in) ? 39 + k : -1;
+    if (k < 71) return k - 32;
+    return -1;
+}
+
+// W rows [row0, row0 + 64) x [0, K_src) -> hi/lo in the [k/4][64][4] layout, zero padded to K_pad columns / n_rows rows
+__device__ void tcf_stage_weight(const float *__restrict__ W, int row0, int n_rows, int K_src, int K_pad, float *hi, float *lo,
+                                 bool layer0 = false) {
+    for (int i = threadIdx.x; i < K_pad * NICER_W; i += blockDim.x) {
+        const int n = i / K_pad, k = i - n * K_pad;
+        const int ksrc = layer0 ? tcf_col_src(k, K_src) : (k < K_src ? k : -1);
+        const float w = (ksrc >= 0 && n < n_rows) ? W[(size_t)(row0 + n) * K_src + ksrc] : 0.f;
+        const float h = tc::tf32_hi(w);
+        const int dst = ((k >> 2) * NICER_W + n) * 4 + (k & 3);
+        hi[dst] = h;
+        lo[dst] = w - h;
+    }
+}
+
+struct Tile {
+    uint32_t tmem;        // TMEM address of the tile's column 0, lane 0
+    uint32_t lane_base;   // + this warp's lane quarter
+    uint64_t *bar;
+    uint32_t parity;
+    int id;               // named barrier id (1 or 2)
+    bool leader;
+};
+
+__device__ __forceinline__ void tile_sync(const Tile &t) { asm volatile("bar.sync %0, 128;" ::"r"(t.id) : "memory"); }
+
+// D[128 x N] = A[128 x K] * B^T, A = (hi, lo) column ranges of the tile, B from shared memory.
+// transposed == false: B = W ([64 rows][K]), K-major.   transposed == true: B = W^T ([N rows of k][K = 64 j]), MN-major.
+__device__ __forceinline__ void tile_gemm(Tile &t, uint32_t whi, uint32_t wlo, int K, int N, bool transposed) {
+    tc::wait_st();
+    tc::fence_before_sync();
+    tile_sync(t);
+    if (t.leader) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)N, 0u, transposed ? 1u : 0u);
+        const uint32_t step = transposed ? 128u : 2u * CHUNK_BYTES;
+        const uint32_t lbo = transposed ? 128u : CHUNK_BYTES, sbo = transposed ? CHUNK_BYTES : 128u;
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const uint64_t bhi = tc::smem_desc(whi + (uint32_t)ks * step, lbo, sbo);
+            const uint64_t blo = tc::smem_desc(wlo + (uint32_t)ks * step, lbo, sbo);
+            const uint32_t ahi = t.tmem + TCF_AHI + ks * 8, alo = t.tmem + TCF_ALO + ks * 8;
+            tc::mma_tf32_ts(t.tmem + TCF_D, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
+            tc::mma_tf32_ts(t.tmem + TCF_D, alo, bhi, idesc, 1u);
+            tc::mma_tf32_ts(t.tmem + TCF_D, ahi, blo, idesc, 1u);
+        }
+        tc::mma_commit(t.bar);
+    }
+    tc::mbar_wait(t.bar, t.parity);
+    t.parity ^= 1u;
+    __syncwarp();
+    tc::fence_after_sync();
+}
+
+__device__ __forceinline__ void ld_d8(const Tile &t, int c8, float v[8]) { tc::tmem_ld8(t.lane_base + TCF_D + c8 * 8, v); }
+__device__ __forceinline__ void st_a8(const Tile &t, int c8, const float v[8]) {
+    tc::tmem_st8_split(t.lane_base + TCF_AHI + c8 * 8, t.lane_base + TCF_ALO + c8 * 8, v);
+}
+
+// C (2, 4 or 8) consecutive A columns starting at a multiple of C, hi/lo split
+template <int C>
+__device__ __forceinline__ void st_a_small(const Tile &t, int col, const float v[C]) {
+    float h[C], l[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) { h[i] = tc::tf32_hi(v[i]); l[i] = v[i] - h[i]; }
+    const uint32_t ahi = t.lane_base + TCF_AHI + col, alo = t.lane_base + TCF_ALO + col;
+    if constexpr (C == 8) {
+        tc::tmem_st8(ahi, h);
+        tc::tmem_st8(alo, l);
+    } else if constexpr (C == 4) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ahi), "r"(__float_as_uint(h[0])),
+                     "r"(__float_as_uint(h[1])), "r"(__float_as_uint(h[2])), "r"(__float_as_uint(h[3])) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(alo), "r"(__float_as_uint(l[0])),
+                     "r"(__float_as_uint(l[1])), "r"(__float_as_uint(l[2])), "r"(__float_as_uint(l[3])) : "memory");
+    } else {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(ahi), "r"(__float_as_uint(h[0])),
+                     "r"(__float_as_uint(h[1])) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(alo), "r"(__float_as_uint(l[0])),
+                     "r"(__float_as_uint(l[1])) : "memory");
+    }
+}
+
+struct TcfShared {
+    uint64_t bars[2];
+    uint32_t tmem_slot;
+};
+
+// common per-CTA setup: weights, biases, levels, barriers, TMEM. Returns the tile of the calling thread.
+template <int C>
+__device__ __forceinline__ Tile tcf_setup(const nicer_sdf_net_t &net, const LevelScales &ls, const TcfLayout &lay, float *smem,
+                                          TcfShared &sh, LevelInfo *&lv) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int n = (int)net.n_hidden, L = (int)net.grid.L;
+    const int d_in = 3 + 6 * (int)net.multires + L * C;
+    for (int l = 0; l < n; ++l) {
+        tcf_stage_weight(net.W[l], 0, NICER_W, l == 0 ? d_in : NICER_W, l == 0 ? TCF_K0 : NICER_W, smem + lay.w_hi[l], smem + lay.w_lo[l], l == 0);
+        for (int i = tid; i < NICER_W; i += TCF_THREADS) smem[lay.bias[l] + i] = net.b[l][i];
+    }
+    const int nfeat = (int)net.d_out - 1;
+    tcf_stage_weight(net.W[n], 1, nfeat, NICER_W, NICER_W, smem + lay.w_hi[n], smem + lay.w_lo[n]);
+    for (int i = tid; i < NICER_W; i += TCF_THREADS) {
+        smem[lay.bias[n] + i] = (i < nfeat) ? net.b[n][1 + i] : 0.f;
+        smem[lay.wl_sdf + i] = net.W[n][i];
+    }
+    lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
+    for (int l = tid; l < L; l += TCF_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    if (tid == 0) { tc::mbar_init(&sh.bars[0], 1); tc::mbar_init(&sh.bars[1], 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc(&sh.tmem_slot, TCF_TMEM);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    Tile t;
+    const int tile = tid >> 7;
+    t.tmem = sh.tmem_slot + (uint32_t)tile * TCF_TILE_COLS;
+    t.lane_base = t.tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    t.bar = &sh.bars[tile];
+    t.parity = 0;
+    t.id = 1 + tile;
+    t.leader = (tid & 127) == 0;
+    return t;
+}
+
+template <int C>
+__global__ void __launch_bounds__(TCF_THREADS, 1)
+sdf_forward_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfLayout lay, const float *__restrict__ X,
+                      uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *grad, float *Z, float *R, float *DYDX) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ TcfShared sh;
+    LevelInfo *lv;
+    Tile t = tcf_setup<C>(net, ls, lay, smem, sh, lv);
+    const int n = (int)net.n_hidden, L = (int)net.grid.L;
+    const size_t Ps = P;
+    const float df = net.grid.divide_factor;
+    const bool accumulate = (flags & NICER_SDF_ACCUMULATE) != 0;
+    const bool want_feat = (flags & NICER_SDF_NO_FEAT) == 0;
+    const float *wl = smem + lay.wl_sdf;
+    const float bl_sdf = net.b[n][0];
+
+    const uint32_t tiles = (P + 127u) / 128u;
+    // tile index space: CTA b handles tiles 2*b + {0,1}, 2*(b+grid) + {0,1}, ...
+    for (uint32_t tt = blockIdx.x * 2 + (threadIdx.x >> 7); tt < ((tiles + 1u) & ~1u); tt += gridDim.x * 2) {
+        uint32_t p = tt * 128u + (threadIdx.x & 127);
+        const bool valid = p < P;
+        if (!valid) p = P - 1;
+        const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+        float u[3];
+        to_unit(x, df, u);
+        // ---------------- network input -> A   (columns: [32 grid | 39 PE | pad])
+        {
+            float pe[48];
+            pe[0] = x[0]; pe[1] = x[1]; pe[2] = x[2];
+            float fr = 1.0f;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float s, c;
+                    sincosf(x[d] * fr, &s, &c);
+                    pe[3 + 6 * f + d] = s;
+                    pe[3 + 6 * f + 3 + d] = c;
+                }
+                fr *= 2.0f;
+            }
+#pragma unroll
+            for (int k = 39; k < 48; ++k) pe[k] = 0.f;
+#pragma unroll
+            for (int c8 = 0; c8 < 6; ++c8) st_a8(t, 4 + c8, &pe[c8 * 8]);      // columns 32..79
+        }
+#pragma unroll
+        for (int l = 0; l < 32 / C; ++l) {
+            float feat[C], dfeat[3][C];
+            if (l < L) {
+                encode_level<C, true>(net.grid.table, lv[l], u, feat, dfeat);
+                if (valid) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p] = dfeat[d][c];
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) feat[c] = 0.f;
+            }
+            st_a_small<C>(t, l * C, feat);
+        }
+        // ---------------- hidden layers
+        float q[NICER_W];       // q_n = W_n[0,:] * sp'(z_n), kept for the gradient pass
+        float s_out = bl_sdf;
+        for (int l = 0; l < n; ++l) {
+            tile_gemm(t, tc::smem_u32(smem + lay.w_hi[l]), tc::smem_u32(smem + lay.w_lo[l]), l == 0 ? TCF_K0 : NICER_W, NICER_W, false);
+            const float *bias = smem + lay.bias[l];
+            const bool last = (l == n - 1);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float v[8];
+                ld_d8(t, c8, v);
+                tc::wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = c8 * 8 + i;
+                    const float z = v[i] + bias[j];
+                    if (valid) Z[((size_t)l * NICER_W + j) * Ps + p] = z;
+                    const SpEval sp = sp_eval(z);
+                    v[i] = sp.a;
+                    if (last) { s_out += wl[j] * sp.a; q[j] = wl[j] * sp.s1; }
+                }
+                st_a8(t, c8, v);
+            }
+        }
+        if (valid) { if (accumulate) sdf[p] += s_out; else sdf[p] = s_out; }
+        // ---------------- feature head
+        if (want_feat) {
+            tile_gemm(t, tc::smem_u32(smem + lay.w_hi[n]), tc::smem_u32(smem + lay.w_lo[n]), NICER_W, NICER_W, false);
+            const float *bias = smem + lay.bias[n];
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float v[8];
+                ld_d8(t, c8, v);
+                tc::wait_ld();
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int j = c8 * 8 + i;
+                        float *dst = feat_fm + (size_t)j * Ps + p;
+                        const float f = v[i] + bias[j];
+                        if (accumulate) *dst += f; else *dst = f;
+                    }
+                }
+            }
+        }
+        // ---------------- gradient pass
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) st_a8(t, c8, &q[c8 * 8]);
+        for (int l = n - 1; l >= 1; --l) {
+            tile_gemm(t, tc::smem_u32(smem + lay.w_hi[l]), tc::smem_u32(smem + lay.w_lo[l]), NICER_W, NICER_W, true);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float v[8];
+                ld_d8(t, c8, v);
+                tc::wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const size_t o = ((size_t)(l - 1) * NICER_W + c8 * 8 + i) * Ps + p;
+                    if (valid) R[o] = v[i];
+                    v[i] *= dsoftplus100(Z[o]);
+                }
+                st_a8(t, c8, v);
+            }
+        }
+        tile_gemm(t, tc::smem_u32(smem + lay.w_hi[0]), tc::smem_u32(smem + lay.w_lo[0]), NICER_W, TCF_K0, true);
+        float g[3];
+        {
+            float rp[40];   // PE part: columns 32..71
+#pragma unroll
+            for (int c8 = 0; c8 < 5; ++c8) ld_d8(t, 4 + c8, &rp[c8 * 8]);
+            tc::wait_ld();
+            g[0] = rp[0]; g[1] = rp[1]; g[2] = rp[2];
+            float fr = 1.0f;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float s, c;
+                    sincosf(x[d] * fr, &s, &c);
+                    g[d] += fr * (c * rp[3 + 6 * f + d] - s * rp[3 + 6 * f + 3 + d]);
+                }
+                fr *= 2.0f;
+            }
+            float gu[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                float rh[8];    // grid part: columns 0..31
+                ld_d8(t, c8, rh);
+                tc::wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = c8 * 8 + i;
+                    if (k < L * C) {
+                        const int l = k / C, c = k % C;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) gu[d] += rh[i] * DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p];
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) g[d] += gu[d] / 2.0f / df;
+        }
+        if (valid) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (accumulate) grad[3 * (size_t)p + d] += g[d]; else grad[3 * (size_t)p + d] = g[d];
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
+}
+
+int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
+                          float *grad, float *Z, float *R, float *DYDX, cudaStream_t st) {
+    TcfLayout lay = tcf_layout((int)net->n_hidden);
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
+    const size_t smem = (size_t)lay.total_floats * sizeof(float);
+    const uint32_t pairs = div_up(div_up(P, 128), 2);
+    const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
+#define LAUNCH(CC)                                                                                                    \
+    do {                                                                                                              \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
+                   "nicer_sdf_forward(tc)");                                                                          \
+        sdf_forward_tc_kernel<CC><<<grid, TCF_THREADS, smem, st>>>(*net, ls, lay, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX); \
+    } while (0)
+    switch (net->grid.C) {
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        default: LAUNCH(8); break;
+    }
+#undef LAUNCH
+    NICER_CHECK_LAUNCH("nicer_sdf_forward(tc)");
+    return 0;
+}
+
+}  // namespace nicer
