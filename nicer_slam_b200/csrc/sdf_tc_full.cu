@@ -4,9 +4,11 @@
 // tcgen05.mma kind::tf32 with the 3xTF32 split:
 //   * one thread = one point = one TMEM lane; activations / adjoints are written with tcgen05.st as the A operand
 //     (hi and lo column ranges), accumulator rows are read back with tcgen05.ld.32x32b by the same thread;
-//   * weights (hi, lo) live in shared memory once per CTA in the layout [k/4][64 rows][4]: read K-major
-//     (LBO = 1024 B, SBO = 128 B) it is W for the forward products, read MN-major (LBO = 128 B, SBO = 1024 B) the very
-//     same bytes are W^T for the gradient chain r_{l-1} = W_{l-1}^T q_l;
+//   * weights (hi, lo) live in shared memory once per CTA in the UMMA K-major no-swizzle layout [k/4][rows][4]
+//     (LBO = rows*16 B between the two 16-byte K-chunks of a step, SBO = 128 B between 8-row groups).  tcgen05 has no
+//     interleaved MN-major form for 32-bit operands, so the transposed products of the gradient chain
+//     r_{l-1} = W_{l-1}^T q_l use separately staged K-major copies of W^T; to fit shared memory the pass is split in
+//     two kernels: A (layers + feature head, saves Z) and B (gradient chain from Z, saves R, emits d sdf/dx);
 //   * a CTA holds two independent 128-point tiles (256 threads) that share the weights and overlap each other's
 //     MMA and epilogue phases; tiles synchronise on named barriers and one mbarrier each.
 #include "common.cuh"
@@ -20,25 +22,65 @@ constexpr int TCF_K0 = 80;          // layer-0 input columns, zero padded (d_in 
 constexpr int TCF_AHI = 0, TCF_ALO = 80, TCF_D = 160, TCF_TILE_COLS = 256, TCF_TMEM = 512;
 constexpr uint32_t CHUNK_BYTES = NICER_W * 16;   // one 4-float K-chunk of all 64 rows
 
-struct TcfLayout {
-    int w_hi[5], w_lo[5], bias[5];   // index l < n: W_l (hidden producing); index n: feature head W_n[1:, :]
+// One staged B operand (hi/lo) of a kernel
+struct MatSpec {
+    int layer;       // index into net.W
+    int row0, w_rows, w_cols;   // source window: rows [row0, row0 + w_rows) of W (row-major, w_cols columns)
+    int rows, K;     // operand shape: `rows` rows (N of the MMA), K contraction columns (multiple of 8)
+    int transposed, layer0;
+    int hi, lo;      // float offsets in dynamic shared memory
+};
+
+struct TcfPlan {
+    MatSpec m[5];
+    int n_mats;
+    int bias[5];     // float offsets of per-layer biases (kernel A), -1 unused
     int wl_sdf, lv, total_floats;
 };
 
-static TcfLayout tcf_layout(int n_hidden) {
-    TcfLayout s;
+// kernel A: W_0 .. W_{n-1} (forward) + feature head W_n[1:, :]
+static TcfPlan plan_a(const nicer_sdf_net_t *net) {
+    TcfPlan pl;
+    const int n = (int)net->n_hidden, d_in = 3 + 6 * (int)net->multires + (int)(net->grid.L * net->grid.C);
     int o = 0;
-    for (int l = 0; l < 5; ++l) {
-        const int K = (l == 0) ? TCF_K0 : NICER_W;
-        const bool used = l <= n_hidden;
-        s.w_hi[l] = o; if (used) o += K * NICER_W;
-        s.w_lo[l] = o; if (used) o += K * NICER_W;
-        s.bias[l] = o; if (used) o += NICER_W;
+    pl.n_mats = n + 1;
+    for (int l = 0; l <= n; ++l) {
+        MatSpec &m = pl.m[l];
+        m.layer = l; m.transposed = 0; m.layer0 = (l == 0);
+        m.row0 = (l == n) ? 1 : 0;
+        m.w_rows = (l == n) ? (int)net->d_out - 1 : NICER_W;
+        m.w_cols = (l == 0) ? d_in : NICER_W;
+        m.rows = NICER_W; m.K = (l == 0) ? TCF_K0 : NICER_W;
+        m.hi = o; o += m.rows * m.K;
+        m.lo = o; o += m.rows * m.K;
+        pl.bias[l] = o; o += NICER_W;
     }
-    s.wl_sdf = o; o += NICER_W;
-    s.lv = o; o += NICER_MAX_LEVELS * 4;
-    s.total_floats = o;
-    return s;
+    for (int l = n + 1; l < 5; ++l) pl.bias[l] = -1;
+    pl.wl_sdf = o; o += NICER_W;
+    pl.lv = o; o += NICER_MAX_LEVELS * 4;
+    pl.total_floats = o;
+    return pl;
+}
+
+// kernel B: W_{n-1}^T .. W_1^T (64 x 64) and W_0^T (80 rows x 64)
+static TcfPlan plan_b(const nicer_sdf_net_t *net) {
+    TcfPlan pl;
+    const int n = (int)net->n_hidden, d_in = 3 + 6 * (int)net->multires + (int)(net->grid.L * net->grid.C);
+    int o = 0;
+    pl.n_mats = n;
+    for (int l = 0; l < n; ++l) {       // m[l] = W_l^T
+        MatSpec &m = pl.m[l];
+        m.layer = l; m.transposed = 1; m.layer0 = (l == 0);
+        m.row0 = 0; m.w_rows = NICER_W; m.w_cols = (l == 0) ? d_in : NICER_W;
+        m.rows = (l == 0) ? TCF_K0 : NICER_W; m.K = NICER_W;
+        m.hi = o; o += m.rows * m.K;
+        m.lo = o; o += m.rows * m.K;
+    }
+    for (int l = 0; l < 5; ++l) pl.bias[l] = -1;
+    pl.wl_sdf = o; o += NICER_W;
+    pl.lv = o; o += NICER_MAX_LEVELS * 4;
+    pl.total_floats = o;
+    return pl;
 }
 
 // Column order of the layer-0 operand inside the kernel: [32 grid features | 39 PE values | zero padding] (grid
@@ -50,15 +92,19 @@ __device__ __forceinline__ int tcf_col_src(int k, int d_in) {
     return -1;
 }
 
-// W rows [row0, row0 + 64) x [0, K_src) -> hi/lo in the [k/4][64][4] layout, zero padded to K_pad columns / n_rows rows
-__device__ void tcf_stage_weight(const float *__restrict__ W, int row0, int n_rows, int K_src, int K_pad, float *hi, float *lo,
-                                 bool layer0 = false) {
-    for (int i = threadIdx.x; i < K_pad * NICER_W; i += blockDim.x) {
+// Generic staging of a B operand with `rows` rows and K_pad contraction columns into hi/lo [k/4][rows][4].
+//   transposed == false: B[n][k] = W[row0 + n][col(k)]   (W row-major [*, K_src]; layer0: col() permutes, see tcf_col_src)
+//   transposed == true : B[n][k] = W[row0 + k][col(n)]   (B = W^T: rows index W's columns, contraction over W's rows)
+__device__ void tcf_stage(const float *__restrict__ W, int row0, int w_rows, int w_cols, int rows, int K_pad, bool transposed,
+                          bool layer0, float *hi, float *lo) {
+    for (int i = threadIdx.x; i < K_pad * rows; i += blockDim.x) {
         const int n = i / K_pad, k = i - n * K_pad;
-        const int ksrc = layer0 ? tcf_col_src(k, K_src) : (k < K_src ? k : -1);
-        const float w = (ksrc >= 0 && n < n_rows) ? W[(size_t)(row0 + n) * K_src + ksrc] : 0.f;
+        const int wr = transposed ? k : n;
+        const int wc_raw = transposed ? n : k;
+        const int wc = layer0 ? tcf_col_src(wc_raw, w_cols) : (wc_raw < w_cols ? wc_raw : -1);
+        const float w = (wc >= 0 && wr < w_rows) ? W[(size_t)(row0 + wr) * w_cols + wc] : 0.f;
         const float h = tc::tf32_hi(w);
-        const int dst = ((k >> 2) * NICER_W + n) * 4 + (k & 3);
+        const int dst = ((k >> 2) * rows + n) * 4 + (k & 3);
         hi[dst] = h;
         lo[dst] = w - h;
     }
@@ -75,20 +121,18 @@ struct Tile {
 
 __device__ __forceinline__ void tile_sync(const Tile &t) { asm volatile("bar.sync %0, 128;" ::"r"(t.id) : "memory"); }
 
-// D[128 x N] = A[128 x K] * B^T, A = (hi, lo) column ranges of the tile, B from shared memory.
-// transposed == false: B = W ([64 rows][K]), K-major.   transposed == true: B = W^T ([N rows of k][K = 64 j]), MN-major.
-__device__ __forceinline__ void tile_gemm(Tile &t, uint32_t whi, uint32_t wlo, int K, int N, bool transposed) {
+// D[128 x N] = A[128 x K] * B^T:  A = (hi, lo) column ranges of the tile (TMEM), B = N rows x K, K-major in shared memory
+__device__ __forceinline__ void tile_gemm(Tile &t, uint32_t whi, uint32_t wlo, int K, int N) {
     tc::wait_st();
     tc::fence_before_sync();
     tile_sync(t);
     if (t.leader) {
         tc::fence_after_sync();
-        const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)N, 0u, transposed ? 1u : 0u);
-        const uint32_t step = transposed ? 128u : 2u * CHUNK_BYTES;
-        const uint32_t lbo = transposed ? 128u : CHUNK_BYTES, sbo = transposed ? CHUNK_BYTES : 128u;
+        const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)N);
+        const uint32_t chunk = (uint32_t)N * 16u;
         for (int ks = 0; ks < K / 8; ++ks) {
-            const uint64_t bhi = tc::smem_desc(whi + (uint32_t)ks * step, lbo, sbo);
-            const uint64_t blo = tc::smem_desc(wlo + (uint32_t)ks * step, lbo, sbo);
+            const uint64_t bhi = tc::smem_desc(whi + (uint32_t)ks * 2u * chunk, chunk, 128u);
+            const uint64_t blo = tc::smem_desc(wlo + (uint32_t)ks * 2u * chunk, chunk, 128u);
             const uint32_t ahi = t.tmem + TCF_AHI + ks * 8, alo = t.tmem + TCF_ALO + ks * 8;
             tc::mma_tf32_ts(t.tmem + TCF_D, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
             tc::mma_tf32_ts(t.tmem + TCF_D, alo, bhi, idesc, 1u);
@@ -135,24 +179,23 @@ struct TcfShared {
     uint32_t tmem_slot;
 };
 
-// common per-CTA setup: weights, biases, levels, barriers, TMEM. Returns the tile of the calling thread.
-template <int C>
-__device__ __forceinline__ Tile tcf_setup(const nicer_sdf_net_t &net, const LevelScales &ls, const TcfLayout &lay, float *smem,
+// common per-CTA setup: staged operands, biases, levels, barriers, TMEM. Returns the tile of the calling thread.
+__device__ __forceinline__ Tile tcf_setup(const nicer_sdf_net_t &net, const LevelScales &ls, const TcfPlan &pl, float *smem,
                                           TcfShared &sh, LevelInfo *&lv) {
     const int tid = threadIdx.x, warp = tid >> 5;
     const int n = (int)net.n_hidden, L = (int)net.grid.L;
-    const int d_in = 3 + 6 * (int)net.multires + L * C;
-    for (int l = 0; l < n; ++l) {
-        tcf_stage_weight(net.W[l], 0, NICER_W, l == 0 ? d_in : NICER_W, l == 0 ? TCF_K0 : NICER_W, smem + lay.w_hi[l], smem + lay.w_lo[l], l == 0);
-        for (int i = tid; i < NICER_W; i += TCF_THREADS) smem[lay.bias[l] + i] = net.b[l][i];
+    for (int i = 0; i < pl.n_mats; ++i) {
+        const MatSpec &m = pl.m[i];
+        tcf_stage(net.W[m.layer], m.row0, m.w_rows, m.w_cols, m.rows, m.K, m.transposed != 0, m.layer0 != 0, smem + m.hi, smem + m.lo);
     }
     const int nfeat = (int)net.d_out - 1;
-    tcf_stage_weight(net.W[n], 1, nfeat, NICER_W, NICER_W, smem + lay.w_hi[n], smem + lay.w_lo[n]);
-    for (int i = tid; i < NICER_W; i += TCF_THREADS) {
-        smem[lay.bias[n] + i] = (i < nfeat) ? net.b[n][1 + i] : 0.f;
-        smem[lay.wl_sdf + i] = net.W[n][i];
+    for (int l = 0; l <= n; ++l) {
+        if (pl.bias[l] < 0) continue;
+        for (int i = tid; i < NICER_W; i += TCF_THREADS)
+            smem[pl.bias[l] + i] = (l < n) ? net.b[l][i] : ((i < nfeat) ? net.b[n][1 + i] : 0.f);
     }
-    lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
+    for (int i = tid; i < NICER_W; i += TCF_THREADS) smem[pl.wl_sdf + i] = net.W[n][i];
+    lv = reinterpret_cast<LevelInfo *>(smem + pl.lv);
     for (int l = tid; l < L; l += TCF_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
     if (tid == 0) { tc::mbar_init(&sh.bars[0], 1); tc::mbar_init(&sh.bars[1], 1); tc::fence_mbar_init(); }
     if (warp == 0) tc::tmem_alloc(&sh.tmem_slot, TCF_TMEM);
@@ -171,20 +214,24 @@ __device__ __forceinline__ Tile tcf_setup(const nicer_sdf_net_t &net, const Leve
     return t;
 }
 
+__device__ __forceinline__ void mat_gemm(Tile &t, const TcfPlan &pl, int i, float *smem) {
+    tile_gemm(t, tc::smem_u32(smem + pl.m[i].hi), tc::smem_u32(smem + pl.m[i].lo), pl.m[i].K, pl.m[i].rows);
+}
+
 template <int C>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
-sdf_forward_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfLayout lay, const float *__restrict__ X,
-                      uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *grad, float *Z, float *R, float *DYDX) {
+sdf_forward_tc_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
+                      uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z, float *DYDX) {
     extern __shared__ __align__(16) float smem[];
     __shared__ TcfShared sh;
     LevelInfo *lv;
-    Tile t = tcf_setup<C>(net, ls, lay, smem, sh, lv);
+    Tile t = tcf_setup(net, ls, pl, smem, sh, lv);
     const int n = (int)net.n_hidden, L = (int)net.grid.L;
     const size_t Ps = P;
     const float df = net.grid.divide_factor;
     const bool accumulate = (flags & NICER_SDF_ACCUMULATE) != 0;
     const bool want_feat = (flags & NICER_SDF_NO_FEAT) == 0;
-    const float *wl = smem + lay.wl_sdf;
+    const float *wl = smem + pl.wl_sdf;
     const float bl_sdf = net.b[n][0];
 
     const uint32_t tiles = (P + 127u) / 128u;
@@ -235,11 +282,10 @@ sdf_forward_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const Tcf
             st_a_small<C>(t, l * C, feat);
         }
         // ---------------- hidden layers
-        float q[NICER_W];       // q_n = W_n[0,:] * sp'(z_n), kept for the gradient pass
         float s_out = bl_sdf;
         for (int l = 0; l < n; ++l) {
-            tile_gemm(t, tc::smem_u32(smem + lay.w_hi[l]), tc::smem_u32(smem + lay.w_lo[l]), l == 0 ? TCF_K0 : NICER_W, NICER_W, false);
-            const float *bias = smem + lay.bias[l];
+            mat_gemm(t, pl, l, smem);
+            const float *bias = smem + pl.bias[l];
             const bool last = (l == n - 1);
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
@@ -253,7 +299,7 @@ sdf_forward_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const Tcf
                     if (valid) Z[((size_t)l * NICER_W + j) * Ps + p] = z;
                     const SpEval sp = sp_eval(z);
                     v[i] = sp.a;
-                    if (last) { s_out += wl[j] * sp.a; q[j] = wl[j] * sp.s1; }
+                    if (last) s_out += wl[j] * sp.a;
                 }
                 st_a8(t, c8, v);
             }
@@ -261,8 +307,8 @@ sdf_forward_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const Tcf
         if (valid) { if (accumulate) sdf[p] += s_out; else sdf[p] = s_out; }
         // ---------------- feature head
         if (want_feat) {
-            tile_gemm(t, tc::smem_u32(smem + lay.w_hi[n]), tc::smem_u32(smem + lay.w_lo[n]), NICER_W, NICER_W, false);
-            const float *bias = smem + lay.bias[n];
+            mat_gemm(t, pl, n, smem);
+            const float *bias = smem + pl.bias[n];
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 float v[8];
@@ -279,11 +325,45 @@ sdf_forward_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const Tcf
                 }
             }
         }
-        // ---------------- gradient pass
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
+}
+
+// Kernel B: gradient chain  q_n = W_n[0,:] * sp'(z_n),  r_{l-1} = W_{l-1}^T q_l,  q_l = r_l * sp'(z_l),  g = J^T r_0
+// from the saved pre-activations Z; saves R (adjoints r_l, l < n) and emits d sdf/dx.
+template <int C>
+__global__ void __launch_bounds__(TCF_THREADS, 1)
+sdf_forward_tc_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
+                        uint32_t P, uint32_t flags, float *grad, const float *Z, float *R, const float *DYDX) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ TcfShared sh;
+    LevelInfo *lv;
+    Tile t = tcf_setup(net, ls, pl, smem, sh, lv);
+    const int n = (int)net.n_hidden, L = (int)net.grid.L;
+    const size_t Ps = P;
+    const float df = net.grid.divide_factor;
+    const bool accumulate = (flags & NICER_SDF_ACCUMULATE) != 0;
+    const float *wl = smem + pl.wl_sdf;
+    const uint32_t tiles = (P + 127u) / 128u;
+    for (uint32_t tt = blockIdx.x * 2 + (threadIdx.x >> 7); tt < ((tiles + 1u) & ~1u); tt += gridDim.x * 2) {
+        uint32_t p = tt * 128u + (threadIdx.x & 127);
+        const bool valid = p < P;
+        if (!valid) p = P - 1;
+        // q_n -> A
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) st_a8(t, c8, &q[c8 * 8]);
+        for (int c8 = 0; c8 < 8; ++c8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = c8 * 8 + i;
+                v[i] = wl[j] * dsoftplus100(Z[((size_t)(n - 1) * NICER_W + j) * Ps + p]);
+            }
+            st_a8(t, c8, v);
+        }
         for (int l = n - 1; l >= 1; --l) {
-            tile_gemm(t, tc::smem_u32(smem + lay.w_hi[l]), tc::smem_u32(smem + lay.w_lo[l]), NICER_W, NICER_W, true);
+            mat_gemm(t, pl, l, smem);           // r_l = W_l^T q_{l+1}
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 float v[8];
@@ -298,7 +378,8 @@ sdf_forward_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const Tcf
                 st_a8(t, c8, v);
             }
         }
-        tile_gemm(t, tc::smem_u32(smem + lay.w_hi[0]), tc::smem_u32(smem + lay.w_lo[0]), NICER_W, TCF_K0, true);
+        mat_gemm(t, pl, 0, smem);               // r_0 = W_0^T q_1   (80 columns: [32 grid | 39 PE | pad])
+        const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
         float g[3];
         {
             float rp[40];   // PE part: columns 32..71
@@ -350,16 +431,19 @@ sdf_forward_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const Tcf
 
 int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
                           float *grad, float *Z, float *R, float *DYDX, cudaStream_t st) {
-    TcfLayout lay = tcf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
-    const size_t smem = (size_t)lay.total_floats * sizeof(float);
     const uint32_t pairs = div_up(div_up(P, 128), 2);
     const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
-#define LAUNCH(CC)                                                                                                    \
-    do {                                                                                                              \
-        NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
-                   "nicer_sdf_forward(tc)");                                                                          \
-        sdf_forward_tc_kernel<CC><<<grid, TCF_THREADS, smem, st>>>(*net, ls, lay, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX); \
+    const TcfPlan pa = plan_a(net), pb = plan_b(net);
+    const size_t smem_a = (size_t)pa.total_floats * sizeof(float), smem_b = (size_t)pb.total_floats * sizeof(float);
+#define LAUNCH(CC)                                                                                                      \
+    do {                                                                                                                \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tc_a_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a), \
+                   "nicer_sdf_forward(tc A)");                                                                          \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tc_b_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), \
+                   "nicer_sdf_forward(tc B)");                                                                          \
+        sdf_forward_tc_a_kernel<CC><<<grid, TCF_THREADS, smem_a, st>>>(*net, ls, pa, x, P, flags, sdf, feat_fm, Z, DYDX);   \
+        sdf_forward_tc_b_kernel<CC><<<grid, TCF_THREADS, smem_b, st>>>(*net, ls, pb, x, P, flags, grad, Z, R, DYDX);        \
     } while (0)
     switch (net->grid.C) {
         case 2: LAUNCH(2); break;
