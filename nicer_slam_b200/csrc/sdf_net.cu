@@ -140,6 +140,10 @@ int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, u
 int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
                           float *grad, float *Z, float *R, float *DYDX, cudaStream_t st);
 
+int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
+                           const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
+                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *H0, float *T0, cudaStream_t st);
+
 template <typename K>
 static int prep_kernel(K kernel, size_t smem_bytes, const char *who) {
     NICER_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes), who);
@@ -198,6 +202,9 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
         NICER_FAIL(-1, "nicer_sdf_backward: a required pointer is NULL");
     if (net->n_hidden > 1 && !R) NICER_FAIL(-1, "nicer_sdf_backward: R required for n_hidden > 1");
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_backward: n_hidden > 3 not built");
+    if (tc_enabled() && net->multires == 6)
+        return launch_sdf_backward_tc(net, x, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB, TAN, H0, T0,
+                                      (cudaStream_t)stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);

@@ -20,7 +20,6 @@ namespace nicer {
 constexpr int TCF_THREADS = 256;
 constexpr int TCF_K0 = 80;          // layer-0 input columns, zero padded (d_in <= 71); multiple of 16 so it can be an N
 constexpr int TCF_AHI = 0, TCF_ALO = 80, TCF_D = 160, TCF_TILE_COLS = 256, TCF_TMEM = 512;
-constexpr uint32_t CHUNK_BYTES = NICER_W * 16;   // one 4-float K-chunk of all 64 rows
 
 // One staged B operand (hi/lo) of a kernel
 struct MatSpec {
@@ -77,6 +76,48 @@ static TcfPlan plan_b(const nicer_sdf_net_t *net) {
         m.lo = o; o += m.rows * m.K;
     }
     for (int l = 0; l < 5; ++l) pl.bias[l] = -1;
+    pl.wl_sdf = o; o += NICER_W;
+    pl.lv = o; o += NICER_MAX_LEVELS * 4;
+    pl.total_floats = o;
+    return pl;
+}
+
+// backward kernel T (tangent pass): W_0 .. W_{n-1} (forward orientation)
+static TcfPlan plan_t(const nicer_sdf_net_t *net) {
+    TcfPlan pl = plan_a(net);
+    // same operands as kernel A minus the feature head and the biases: rebuild compactly
+    const int n = (int)net->n_hidden;
+    int o = 0;
+    pl.n_mats = n;
+    for (int l = 0; l < n; ++l) {
+        MatSpec &m = pl.m[l];
+        m.hi = o; o += m.rows * m.K;
+        m.lo = o; o += m.rows * m.K;
+    }
+    for (int l = 0; l < 5; ++l) pl.bias[l] = -1;
+    pl.wl_sdf = o; o += NICER_W;
+    pl.lv = o; o += NICER_MAX_LEVELS * 4;
+    pl.total_floats = o;
+    return pl;
+}
+
+// backward kernel R (reverse pass): m[0..n-1] = W_l^T as in kernel B, m[n] = (W_n[1:, :])^T (feature head transposed)
+static TcfPlan plan_r(const nicer_sdf_net_t *net) {
+    TcfPlan pl = plan_b(net);
+    const int n = (int)net->n_hidden;
+    int o = 0;
+    for (int l = 0; l < n; ++l) {
+        MatSpec &m = pl.m[l];
+        m.hi = o; o += m.rows * m.K;
+        m.lo = o; o += m.rows * m.K;
+    }
+    MatSpec &f = pl.m[n];
+    f.layer = n; f.transposed = 1; f.layer0 = 0;
+    f.row0 = 1; f.w_rows = (int)net->d_out - 1; f.w_cols = NICER_W;
+    f.rows = NICER_W; f.K = NICER_W;
+    f.hi = o; o += f.rows * f.K;
+    f.lo = o; o += f.rows * f.K;
+    pl.n_mats = n + 1;
     pl.wl_sdf = o; o += NICER_W;
     pl.lv = o; o += NICER_MAX_LEVELS * 4;
     pl.total_floats = o;
@@ -452,6 +493,315 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
     }
 #undef LAUNCH
     NICER_CHECK_LAUNCH("nicer_sdf_forward(tc)");
+    return 0;
+}
+
+
+// ================================================================================================ backward
+// Kernel T: tangent pass (forward-mode derivative of the network in direction g_bar = dL/d(d sdf/dx)):
+//   t_0 = J g_bar, u_1 = W_0 t_0, tan_l = u_l * sp'(z_l), u_{l+1} = W_l tan_l
+// and the per-layer buffers the weight-gradient GEMMs and kernel R need: TAN, QB = r_l sp'(z_l), AB = a_l,
+// ZB <- u_l r_l sp''(z_l) (the second-order part of dL/dz_l), T0 (all rows) and the PE rows of H0.
+template <int C>
+__global__ void __launch_bounds__(TCF_THREADS, 1)
+sdf_backward_tc_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
+                         uint32_t P, const float *Z, const float *R, const float *DYDX, const float *g_grad, float *ZB,
+                         float *QB, float *AB, float *TAN, float *H0, float *T0) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ TcfShared sh;
+    LevelInfo *lv;
+    Tile t = tcf_setup(net, ls, pl, smem, sh, lv);
+    const int n = (int)net.n_hidden, L = (int)net.grid.L;
+    const size_t Ps = P;
+    const float df = net.grid.divide_factor;
+    const float *wl = smem + pl.wl_sdf;
+    const uint32_t tiles = (P + 127u) / 128u;
+    for (uint32_t tt = blockIdx.x * 2 + (threadIdx.x >> 7); tt < ((tiles + 1u) & ~1u); tt += gridDim.x * 2) {
+        uint32_t p = tt * 128u + (threadIdx.x & 127);
+        const bool valid = p < P;
+        if (!valid) p = P - 1;
+        const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+        float gg[3] = {0.f, 0.f, 0.f}, ggu[3];
+        if (g_grad) { gg[0] = g_grad[3 * (size_t)p]; gg[1] = g_grad[3 * (size_t)p + 1]; gg[2] = g_grad[3 * (size_t)p + 2]; }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ggu[d] = gg[d] / 2.0f / df;
+        // ---- t_0: PE part (columns 32..70), rows 0..38 of T0 / H0
+        {
+            float tp[48];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                tp[d] = gg[d];
+                if (valid) { T0[(size_t)d * Ps + p] = gg[d]; H0[(size_t)d * Ps + p] = x[d]; }
+            }
+            float fr = 1.0f;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float s, c;
+                    sincosf(x[d] * fr, &s, &c);
+                    const int ks = 3 + 6 * f + d, kc = ks + 3;
+                    const float ts = fr * c * gg[d], tcv = -fr * s * gg[d];
+                    tp[ks] = ts; tp[kc] = tcv;
+                    if (valid) {
+                        T0[(size_t)ks * Ps + p] = ts; H0[(size_t)ks * Ps + p] = s;
+                        T0[(size_t)kc * Ps + p] = tcv; H0[(size_t)kc * Ps + p] = c;
+                    }
+                }
+                fr *= 2.0f;
+            }
+#pragma unroll
+            for (int k = 39; k < 48; ++k) tp[k] = 0.f;
+#pragma unroll
+            for (int c8 = 0; c8 < 6; ++c8) st_a8(t, 4 + c8, &tp[c8 * 8]);
+        }
+        // ---- t_0: grid part (columns 0..31), rows 39.. of T0
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = c8 * 8 + i;
+                float tv = 0.f;
+                if (k < L * C) {
+                    const int l = k / C, c = k % C;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) tv += ggu[d] * DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p];
+                    if (valid) T0[(size_t)(39 + k) * Ps + p] = tv;
+                }
+                v[i] = tv;
+            }
+            st_a8(t, c8, v);
+        }
+        mat_gemm(t, pl, 0, smem);   // u_1 = W_0 t_0
+        for (int l = 1; l <= n; ++l) {
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float v[8];
+                ld_d8(t, c8, v);
+                tc::wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = c8 * 8 + i;
+                    const size_t o = ((size_t)(l - 1) * NICER_W + j) * Ps + p;
+                    const float z = Z[o];
+                    const float r = (l < n) ? R[o] : wl[j];
+                    const SpEval sp = sp_eval(z);
+                    const float u = v[i];
+                    const float tan = u * sp.s1;
+                    if (valid) {
+                        TAN[o] = tan;
+                        QB[o] = r * sp.s1;
+                        AB[o] = sp.a;
+                        ZB[o] = u * r * sp.s2;
+                    }
+                    v[i] = tan;
+                }
+                if (l < n) st_a8(t, c8, v);
+            }
+            if (l < n) mat_gemm(t, pl, l, smem);   // u_{l+1} = W_l tan_l
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
+}
+
+// Kernel R: reverse pass.  abar_n = W_n^T [g_sdf, g_feat],  zbar_l = abar_l sp'(z_l) + ZB_l (second-order part from
+// kernel T),  abar_{l-1} = W_{l-1}^T zbar_l,  hbar_0 = W_0^T zbar_1,  r_0 = W_0^T q_1 (for the second-order terms);
+// writes zbar_l into ZB, the grid rows of H0, scatters first- and second-order grid gradients, accumulates dL/dx.
+template <int C>
+__global__ void __launch_bounds__(TCF_THREADS, 1)
+sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
+                         uint32_t P, const float *Z, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
+                         const float *g_grad, float *grad_x, float *grad_table, float *ZB, const float *QB, float *H0) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ TcfShared sh;
+    LevelInfo *lv;
+    Tile t = tcf_setup(net, ls, pl, smem, sh, lv);
+    const int n = (int)net.n_hidden, L = (int)net.grid.L;
+    const size_t Ps = P;
+    const float df = net.grid.divide_factor;
+    const float *wl = smem + pl.wl_sdf;
+    const uint32_t tiles = (P + 127u) / 128u;
+    for (uint32_t tt = blockIdx.x * 2 + (threadIdx.x >> 7); tt < ((tiles + 1u) & ~1u); tt += gridDim.x * 2) {
+        uint32_t p = tt * 128u + (threadIdx.x & 127);
+        const bool valid = p < P;
+        if (!valid) p = P - 1;
+        const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+        float u[3];
+        to_unit(x, df, u);
+        const float gs = g_sdf ? g_sdf[p] : 0.f;
+        float gg[3] = {0.f, 0.f, 0.f}, ggu[3];
+        if (g_grad) { gg[0] = g_grad[3 * (size_t)p]; gg[1] = g_grad[3 * (size_t)p + 1]; gg[2] = g_grad[3 * (size_t)p + 2]; }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ggu[d] = gg[d] / 2.0f / df;
+        // ---- A = g_feat -> abar_n' = (W_n[1:])^T g_feat
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = g_feat_fm ? g_feat_fm[(size_t)(c8 * 8 + i) * Ps + p] : 0.f;
+            st_a8(t, c8, v);
+        }
+        mat_gemm(t, pl, n, smem);
+        for (int l = n; l >= 1; --l) {
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float v[8];
+                ld_d8(t, c8, v);
+                tc::wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = c8 * 8 + i;
+                    const size_t o = ((size_t)(l - 1) * NICER_W + k) * Ps + p;
+                    const float abar = (l == n) ? v[i] + wl[k] * gs : v[i];
+                    const float zb = abar * dsoftplus100(Z[o]) + ZB[o];
+                    if (valid) ZB[o] = zb;
+                    v[i] = zb;
+                }
+                st_a8(t, c8, v);
+            }
+            mat_gemm(t, pl, l - 1, smem);   // abar_{l-1} = W_{l-1}^T zbar_l   (l == 1: hbar_0, 80 columns)
+        }
+        // ---- hbar_0: PE part -> dL/dx, grid part kept for the scatter
+        float xb[3];
+        float gy1[32];
+        {
+            float hp[40];
+#pragma unroll
+            for (int c8 = 0; c8 < 5; ++c8) ld_d8(t, 4 + c8, &hp[c8 * 8]);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) ld_d8(t, c8, &gy1[c8 * 8]);
+            tc::wait_ld();
+            xb[0] = hp[0]; xb[1] = hp[1]; xb[2] = hp[2];
+            float fr = 1.0f;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float s, c;
+                    sincosf(x[d] * fr, &s, &c);
+                    xb[d] += fr * (c * hp[3 + 6 * f + d] - s * hp[3 + 6 * f + 3 + d]);
+                }
+                fr *= 2.0f;
+            }
+        }
+        // ---- r_0 = W_0^T q_1 (second-order terms)
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = QB[(size_t)(c8 * 8 + i) * Ps + p];
+            st_a8(t, c8, v);
+        }
+        mat_gemm(t, pl, 0, smem);
+        {
+            float rp[40];
+#pragma unroll
+            for (int c8 = 0; c8 < 5; ++c8) ld_d8(t, 4 + c8, &rp[c8 * 8]);
+            tc::wait_ld();
+            float fr = 1.0f;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float s, c;
+                    sincosf(x[d] * fr, &s, &c);
+                    xb[d] += gg[d] * (fr * fr) * (-s * rp[3 + 6 * f + d] - c * rp[3 + 6 * f + 3 + d]);
+                }
+                fr *= 2.0f;
+            }
+        }
+        float xu[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int l = 0; l < 32 / C; ++l) {
+            if (l < L) {
+                float gy2[C];
+                if constexpr (C == 8) {
+                    tc::tmem_ld8(t.lane_base + TCF_D + l * 8, gy2);
+                } else if constexpr (C == 4) {
+                    uint32_t r0, r1, r2, r3;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(t.lane_base + TCF_D + l * 4) : "memory");
+                    gy2[0] = __uint_as_float(r0); gy2[1] = __uint_as_float(r1); gy2[2] = __uint_as_float(r2); gy2[3] = __uint_as_float(r3);
+                } else {
+                    uint32_t r0, r1;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(t.lane_base + TCF_D + l * 2) : "memory");
+                    gy2[0] = __uint_as_float(r0); gy2[1] = __uint_as_float(r1);
+                }
+                tc::wait_ld();
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) xu[d] += gy1[l * C + c] * DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p];
+                const LevelInfo li = lv[l];
+                Cell3 cell = locate3(li, u);
+                float feat[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) feat[c] = 0.f;
+                if (cell.inside && valid) {
+                    uint32_t idx[8];
+                    corner_indices(li, cell, idx);
+                    float wt[8], dw0[8], dw1[8], dw2[8];
+                    corner_weights(cell, wt);
+                    corner_dweights(cell, 0, dw0);
+                    corner_dweights(cell, 1, dw1);
+                    corner_dweights(cell, 2, dw2);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float val[C], v[C];
+                        load_entry<C>(net.grid.table, li, idx[k], val);
+                        const float w2 = dw0[k] * ggu[0] + dw1[k] * ggu[1] + dw2[k] * ggu[2];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            feat[c] += wt[k] * val[c];
+                            v[c] = wt[k] * gy1[l * C + c] + w2 * gy2[c];
+                        }
+                        scatter_entry<C>(grad_table, li, idx[k], v);
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) H0[(size_t)(39 + l * C + c) * Ps + p] = feat[c];
+                }
+            }
+        }
+        if (grad_x && valid) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) grad_x[3 * (size_t)p + d] += xb[d] + xu[d] / 2.0f / df;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
+}
+
+int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
+                           const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
+                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *H0, float *T0, cudaStream_t st) {
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
+    const uint32_t pairs = div_up(div_up(P, 128), 2);
+    const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
+    const TcfPlan pt = plan_t(net), pr = plan_r(net);
+    const size_t smem_t = (size_t)pt.total_floats * sizeof(float), smem_r = (size_t)pr.total_floats * sizeof(float);
+#define LAUNCH(CC)                                                                                                       \
+    do {                                                                                                                 \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_backward_tc_t_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t), \
+                   "nicer_sdf_backward(tc T)");                                                                          \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_backward_tc_r_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r), \
+                   "nicer_sdf_backward(tc R)");                                                                          \
+        sdf_backward_tc_t_kernel<CC><<<grid, TCF_THREADS, smem_t, st>>>(*net, ls, pt, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, H0, T0); \
+        sdf_backward_tc_r_kernel<CC><<<grid, TCF_THREADS, smem_r, st>>>(*net, ls, pr, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, \
+                                                                        grad_table, ZB, QB, H0);                         \
+    } while (0)
+    switch (net->grid.C) {
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        default: LAUNCH(8); break;
+    }
+#undef LAUNCH
+    NICER_CHECK_LAUNCH("nicer_sdf_backward(tc)");
     return 0;
 }
 

@@ -108,7 +108,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float v[8]) {
 }
 
 // 3xTF32 split: hi keeps the top 19 bits (sign, exponent, 10 mantissa bits), lo = a - hi exactly
-__device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
+// (round-to-nearest tf32: |lo| <= 2^-12 |a|, so the hardware's truncation of lo to tf32 costs <= 2^-23 |a|)
+__device__ __forceinline__ float tf32_hi(float a) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a));
+    return __uint_as_float(u);
+}
 
 // write 8 values as (hi, lo) into the two A-operand column ranges
 __device__ __forceinline__ void tmem_st8_split(uint32_t taddr_hi, uint32_t taddr_lo, const float v[8]) {
