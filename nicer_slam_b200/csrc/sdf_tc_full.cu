@@ -162,8 +162,10 @@ struct Tile {
 
 __device__ __forceinline__ void tile_sync(const Tile &t) { asm volatile("bar.sync %0, 128;" ::"r"(t.id) : "memory"); }
 
-// D[128 x N] = A[128 x K] * B^T:  A = (hi, lo) column ranges of the tile (TMEM), B = N rows x K, K-major in shared memory
-__device__ __forceinline__ void tile_gemm(Tile &t, uint32_t whi, uint32_t wlo, int K, int N) {
+// D[128 x N] = A[128 x K] * B^T:  A = (hi, lo) column ranges of the tile (TMEM), B = N rows x K, K-major in shared memory.
+// Split in issue / wait so that the caller can put the global loads its epilogue needs in flight while the MMAs run
+// (the tcgen05 asm statements are compiler barriers for memory operations: loads are not hoisted across them).
+__device__ __forceinline__ void gemm_issue(Tile &t, uint32_t whi, uint32_t wlo, int K, int N) {
     tc::wait_st();
     tc::fence_before_sync();
     tile_sync(t);
@@ -181,10 +183,16 @@ __device__ __forceinline__ void tile_gemm(Tile &t, uint32_t whi, uint32_t wlo, i
         }
         tc::mma_commit(t.bar);
     }
+}
+__device__ __forceinline__ void gemm_wait(Tile &t) {
     tc::mbar_wait(t.bar, t.parity);
     t.parity ^= 1u;
     __syncwarp();
     tc::fence_after_sync();
+}
+__device__ __forceinline__ void tile_gemm(Tile &t, uint32_t whi, uint32_t wlo, int K, int N) {
+    gemm_issue(t, whi, wlo, K, N);
+    gemm_wait(t);
 }
 
 __device__ __forceinline__ void ld_d8(const Tile &t, int c8, float v[8]) { tc::tmem_ld8(t.lane_base + TCF_D + c8 * 8, v); }
@@ -255,8 +263,22 @@ __device__ __forceinline__ Tile tcf_setup(const nicer_sdf_net_t &net, const Leve
     return t;
 }
 
+__device__ __forceinline__ void mat_issue(Tile &t, const TcfPlan &pl, int i, float *smem) {
+    gemm_issue(t, tc::smem_u32(smem + pl.m[i].hi), tc::smem_u32(smem + pl.m[i].lo), pl.m[i].K, pl.m[i].rows);
+}
 __device__ __forceinline__ void mat_gemm(Tile &t, const TcfPlan &pl, int i, float *smem) {
-    tile_gemm(t, tc::smem_u32(smem + pl.m[i].hi), tc::smem_u32(smem + pl.m[i].lo), pl.m[i].K, pl.m[i].rows);
+    mat_issue(t, pl, i, smem);
+    gemm_wait(t);
+}
+// all 64 values of one saved layer row-block for this point (issued together: 64 loads in flight)
+__device__ __forceinline__ void load64(const float *__restrict__ base, size_t row0, size_t Ps, uint32_t p, float v[NICER_W]) {
+#pragma unroll
+    for (int j = 0; j < NICER_W; ++j) v[j] = __ldg(base + (row0 + j) * Ps + p);
+}
+// same through the coherent path (for a buffer the kernel also writes)
+__device__ __forceinline__ void load64_rw(const float *base, size_t row0, size_t Ps, uint32_t p, float v[NICER_W]) {
+#pragma unroll
+    for (int j = 0; j < NICER_W; ++j) v[j] = base[(row0 + j) * Ps + p];
 }
 
 template <int C>
@@ -393,18 +415,22 @@ sdf_forward_tc_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
         const bool valid = p < P;
         if (!valid) p = P - 1;
         // q_n -> A
+        {
+            float zv[NICER_W];
+            load64(Z, (size_t)(n - 1) * NICER_W, Ps, p, zv);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-            float v[8];
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int j = c8 * 8 + i;
-                v[i] = wl[j] * dsoftplus100(Z[((size_t)(n - 1) * NICER_W + j) * Ps + p]);
+                for (int i = 0; i < 8; ++i) v[i] = wl[c8 * 8 + i] * dsoftplus100(zv[c8 * 8 + i]);
+                st_a8(t, c8, v);
             }
-            st_a8(t, c8, v);
         }
         for (int l = n - 1; l >= 1; --l) {
-            mat_gemm(t, pl, l, smem);           // r_l = W_l^T q_{l+1}
+            mat_issue(t, pl, l, smem);          // r_l = W_l^T q_{l+1}
+            float zv[NICER_W];
+            load64(Z, (size_t)(l - 1) * NICER_W, Ps, p, zv);
+            gemm_wait(t);
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 float v[8];
@@ -414,13 +440,17 @@ sdf_forward_tc_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
                 for (int i = 0; i < 8; ++i) {
                     const size_t o = ((size_t)(l - 1) * NICER_W + c8 * 8 + i) * Ps + p;
                     if (valid) R[o] = v[i];
-                    v[i] *= dsoftplus100(Z[o]);
+                    v[i] *= dsoftplus100(zv[c8 * 8 + i]);
                 }
                 st_a8(t, c8, v);
             }
         }
-        mat_gemm(t, pl, 0, smem);               // r_0 = W_0^T q_1   (80 columns: [32 grid | 39 PE | pad])
-        const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+        mat_issue(t, pl, 0, smem);              // r_0 = W_0^T q_1   (80 columns: [32 grid | 39 PE | pad])
+        const float x[3] = {__ldg(X + 3 * (size_t)p), __ldg(X + 3 * (size_t)p + 1), __ldg(X + 3 * (size_t)p + 2)};
+        float dyv[96];
+#pragma unroll
+        for (int k = 0; k < 96; ++k) dyv[k] = (k < L * 3 * C) ? __ldg(DYDX + (size_t)k * Ps + p) : 0.f;
+        gemm_wait(t);
         float g[3];
         {
             float rp[40];   // PE part: columns 32..71
@@ -451,7 +481,7 @@ sdf_forward_tc_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
                     if (k < L * C) {
                         const int l = k / C, c = k % C;
 #pragma unroll
-                        for (int d = 0; d < 3; ++d) gu[d] += rh[i] * DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p];
+                        for (int d = 0; d < 3; ++d) gu[d] += rh[i] * dyv[(l * 3 + d) * C + c];
                     }
                 }
             }
@@ -556,25 +586,31 @@ sdf_backward_tc_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
             for (int c8 = 0; c8 < 6; ++c8) st_a8(t, 4 + c8, &tp[c8 * 8]);
         }
         // ---- t_0: grid part (columns 0..31), rows 39.. of T0
+        {
+            float dyv[96];
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-            float v[8];
+            for (int k = 0; k < 96; ++k) dyv[k] = (k < L * 3 * C) ? __ldg(DYDX + (size_t)k * Ps + p) : 0.f;
+            float tv[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int k = c8 * 8 + i;
-                float tv = 0.f;
-                if (k < L * C) {
-                    const int l = k / C, c = k % C;
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) tv += ggu[d] * DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p];
-                    if (valid) T0[(size_t)(39 + k) * Ps + p] = tv;
-                }
-                v[i] = tv;
+            for (int k = 0; k < 32; ++k) {
+                const int l = k / C, c = k % C;
+                tv[k] = (k < L * C) ? ggu[0] * dyv[(l * 3 + 0) * C + c] + ggu[1] * dyv[(l * 3 + 1) * C + c] + ggu[2] * dyv[(l * 3 + 2) * C + c] : 0.f;
+                if (valid && k < L * C) T0[(size_t)(39 + k) * Ps + p] = tv[k];
             }
-            st_a8(t, c8, v);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) st_a8(t, c8, &tv[c8 * 8]);
         }
-        mat_gemm(t, pl, 0, smem);   // u_1 = W_0 t_0
+        mat_issue(t, pl, 0, smem);   // u_1 = W_0 t_0
         for (int l = 1; l <= n; ++l) {
+            float zv[NICER_W], rv[NICER_W];
+            load64(Z, (size_t)(l - 1) * NICER_W, Ps, p, zv);
+            if (l < n) {
+                load64(R, (size_t)(l - 1) * NICER_W, Ps, p, rv);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NICER_W; ++j) rv[j] = wl[j];
+            }
+            gemm_wait(t);
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 float v[8];
@@ -584,22 +620,20 @@ sdf_backward_tc_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
                 for (int i = 0; i < 8; ++i) {
                     const int j = c8 * 8 + i;
                     const size_t o = ((size_t)(l - 1) * NICER_W + j) * Ps + p;
-                    const float z = Z[o];
-                    const float r = (l < n) ? R[o] : wl[j];
-                    const SpEval sp = sp_eval(z);
+                    const SpEval sp = sp_eval(zv[j]);
                     const float u = v[i];
                     const float tan = u * sp.s1;
                     if (valid) {
                         TAN[o] = tan;
-                        QB[o] = r * sp.s1;
+                        QB[o] = rv[j] * sp.s1;
                         AB[o] = sp.a;
-                        ZB[o] = u * r * sp.s2;
+                        ZB[o] = u * rv[j] * sp.s2;
                     }
                     v[i] = tan;
                 }
                 if (l < n) st_a8(t, c8, v);
             }
-            if (l < n) mat_gemm(t, pl, l, smem);   // u_{l+1} = W_l tan_l
+            if (l < n) mat_issue(t, pl, l, smem);   // u_{l+1} = W_l tan_l
         }
     }
     tc::fence_before_sync();
@@ -644,8 +678,12 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
             for (int i = 0; i < 8; ++i) v[i] = g_feat_fm ? g_feat_fm[(size_t)(c8 * 8 + i) * Ps + p] : 0.f;
             st_a8(t, c8, v);
         }
-        mat_gemm(t, pl, n, smem);
+        mat_issue(t, pl, n, smem);
         for (int l = n; l >= 1; --l) {
+            float zv[NICER_W], cv[NICER_W];
+            load64(Z, (size_t)(l - 1) * NICER_W, Ps, p, zv);
+            load64_rw(ZB, (size_t)(l - 1) * NICER_W, Ps, p, cv);
+            gemm_wait(t);
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 float v[8];
@@ -656,14 +694,19 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
                     const int k = c8 * 8 + i;
                     const size_t o = ((size_t)(l - 1) * NICER_W + k) * Ps + p;
                     const float abar = (l == n) ? v[i] + wl[k] * gs : v[i];
-                    const float zb = abar * dsoftplus100(Z[o]) + ZB[o];
+                    const float zb = abar * dsoftplus100(zv[k]) + cv[k];
                     if (valid) ZB[o] = zb;
                     v[i] = zb;
                 }
                 st_a8(t, c8, v);
             }
-            mat_gemm(t, pl, l - 1, smem);   // abar_{l-1} = W_{l-1}^T zbar_l   (l == 1: hbar_0, 80 columns)
+            mat_issue(t, pl, l - 1, smem);   // abar_{l-1} = W_{l-1}^T zbar_l   (l == 1: hbar_0, 80 columns)
         }
+        float q1[NICER_W], dyv[96];
+        load64(QB, 0, Ps, p, q1);
+#pragma unroll
+        for (int k = 0; k < 96; ++k) dyv[k] = (k < L * 3 * C) ? __ldg(DYDX + (size_t)k * Ps + p) : 0.f;
+        gemm_wait(t);
         // ---- hbar_0: PE part -> dL/dx, grid part kept for the scatter
         float xb[3];
         float gy1[32];
@@ -689,12 +732,7 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
         }
         // ---- r_0 = W_0^T q_1 (second-order terms)
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = QB[(size_t)(c8 * 8 + i) * Ps + p];
-            st_a8(t, c8, v);
-        }
+        for (int c8 = 0; c8 < 8; ++c8) st_a8(t, c8, &q1[c8 * 8]);
         mat_gemm(t, pl, 0, smem);
         {
             float rp[40];
@@ -734,7 +772,7 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
 #pragma unroll
                 for (int c = 0; c < C; ++c)
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) xu[d] += gy1[l * C + c] * DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p];
+                    for (int d = 0; d < 3; ++d) xu[d] += gy1[l * C + c] * dyv[(l * 3 + d) * C + c];
                 const LevelInfo li = lv[l];
                 Cell3 cell = locate3(li, u);
                 float feat[C];
