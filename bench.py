@@ -452,7 +452,10 @@ def kernel_breakdown(step, dev):
     view = torch.randn(P, 3, device=dev)
     stream = torch.cuda.current_stream()
 
-    def timed(fn, n=5):
+    def timed(fn0, n=5):
+        def fn():
+            m.zero_grad(set_to_none=True)      # do not time gradient accumulation into 1 GB .grad buffers
+            fn0()
         fn(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)

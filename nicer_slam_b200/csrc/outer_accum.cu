@@ -71,6 +71,9 @@ outer_accum_kernel(const float *__restrict__ A, uint32_t lda, uint32_t M, const 
     }
 }
 
+int launch_outer_accum_tc(const float *A, uint32_t lda, uint32_t M, const float *B, uint32_t ldb, uint32_t N, uint32_t P, float *C,
+                          uint32_t ldc, float *bias, cudaStream_t st);
+
 }  // namespace nicer
 
 using namespace nicer;
@@ -81,6 +84,10 @@ extern "C" int nicer_outer_accum(const float *A, uint32_t lda, uint32_t M, const
     if (!A || !B || !C) NICER_FAIL(-1, "nicer_outer_accum: NULL pointer");
     if (M > 64 || N > 144) NICER_FAIL(-1, "nicer_outer_accum: M <= 64 and N <= 144 required (got %u, %u)", M, N);
     if (lda < P || ldb < P || ldc < N) NICER_FAIL(-1, "nicer_outer_accum: bad leading dimension");
+    {
+        const int r = launch_outer_accum_tc(A, lda, M, B, ldb, N, P, C, ldc, bias, (cudaStream_t)stream);
+        if (r != 0) return r < 0 ? r : 0;
+    }
     const uint32_t n_tiles = div_up(P, OA_TP);
     uint32_t grid = (uint32_t)(2 * num_sms());
     if (grid > div_up(n_tiles, 4)) grid = div_up(n_tiles, 4);
