@@ -121,6 +121,13 @@ static int check_color_net(const nicer_color_net_t *net, const char *who) {
     return 0;
 }
 
+int launch_color_forward_tc(const nicer_color_net_t *net, const float *x, const float *view, const float *normals, const float *feat_fm,
+                            uint32_t P, float *rgb, float *A_fm, float *DYDX, cudaStream_t st);
+int launch_color_backward_tc(const nicer_color_net_t *net, const float *x, const float *view, const float *normals, uint32_t P,
+                             const float *rgb, const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
+                             float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table, float *ZB, float *OB,
+                             float *H0, cudaStream_t st);
+
 }  // namespace nicer
 
 using namespace nicer;
@@ -131,6 +138,10 @@ extern "C" int nicer_color_forward(const nicer_color_net_t *net, const float *x,
     if (int e = check_color_net(net, "nicer_color_forward")) return e;
     if (P == 0) return 0;
     if (!x || !view || !normals || !feat_fm || !rgb || !A_fm) NICER_FAIL(-1, "nicer_color_forward: NULL pointer");
+    {
+        const int r = launch_color_forward_tc(net, x, view, normals, feat_fm, P, rgb, A_fm, DYDX, (cudaStream_t)stream);
+        if (r != 0) return r < 0 ? r : 0;
+    }
     ColorSmemLayout lay = color_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.table ? net->grid.L : 0, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);
@@ -165,6 +176,11 @@ extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x
         NICER_FAIL(-1, "nicer_color_backward: NULL pointer");
     if (net->grid.table && !net->grid_detached && !grad_table)
         NICER_FAIL(-1, "nicer_color_backward: grad_table required when the grid is not detached");
+    {
+        const int r = launch_color_backward_tc(net, x, view, normals, P, rgb, A_fm, DYDX, g_rgb, grad_x, grad_view, grad_normals,
+                                               grad_feat_fm, grad_table, ZB, OB, H0, (cudaStream_t)stream);
+        if (r != 0) return r < 0 ? r : 0;
+    }
     ColorSmemLayout lay = color_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.table ? net->grid.L : 0, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);

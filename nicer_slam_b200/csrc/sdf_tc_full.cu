@@ -11,24 +11,13 @@
 //     two kernels: A (layers + feature head, saves Z) and B (gradient chain from Z, saves R, emits d sdf/dx);
 //   * a CTA holds two independent 128-point tiles (256 threads) that share the weights and overlap each other's
 //     MMA and epilogue phases; tiles synchronise on named barriers and one mbarrier each.
-#include "common.cuh"
 #include "sdf_sample.cuh"
-#include "tc_common.cuh"
+#include "tc_tile.cuh"
 
 namespace nicer {
 
-constexpr int TCF_THREADS = 256;
 constexpr int TCF_K0 = 80;          // layer-0 input columns, zero padded (d_in <= 71); multiple of 16 so it can be an N
-constexpr int TCF_AHI = 0, TCF_ALO = 80, TCF_D = 160, TCF_TILE_COLS = 256, TCF_TMEM = 512;
-
-// One staged B operand (hi/lo) of a kernel
-struct MatSpec {
-    int layer;       // index into net.W
-    int row0, w_rows, w_cols;   // source window: rows [row0, row0 + w_rows) of W (row-major, w_cols columns)
-    int rows, K;     // operand shape: `rows` rows (N of the MMA), K contraction columns (multiple of 8)
-    int transposed, layer0;
-    int hi, lo;      // float offsets in dynamic shared memory
-};
+constexpr int TCF_ALO = 80, TCF_D = 160;   // TMEM columns of a tile: A hi [0,80), A lo [80,160), accumulator [160,240)
 
 struct TcfPlan {
     MatSpec m[5];
@@ -45,7 +34,7 @@ static TcfPlan plan_a(const nicer_sdf_net_t *net) {
     pl.n_mats = n + 1;
     for (int l = 0; l <= n; ++l) {
         MatSpec &m = pl.m[l];
-        m.layer = l; m.transposed = 0; m.layer0 = (l == 0);
+        m.layer = l; m.transposed = 0; m.colmap = (l == 0) ? 1 : 0; m.col0 = 0;
         m.row0 = (l == n) ? 1 : 0;
         m.w_rows = (l == n) ? (int)net->d_out - 1 : NICER_W;
         m.w_cols = (l == 0) ? d_in : NICER_W;
@@ -69,7 +58,7 @@ static TcfPlan plan_b(const nicer_sdf_net_t *net) {
     pl.n_mats = n;
     for (int l = 0; l < n; ++l) {       // m[l] = W_l^T
         MatSpec &m = pl.m[l];
-        m.layer = l; m.transposed = 1; m.layer0 = (l == 0);
+        m.layer = l; m.transposed = 1; m.colmap = (l == 0) ? 1 : 0; m.col0 = 0;
         m.row0 = 0; m.w_rows = NICER_W; m.w_cols = (l == 0) ? d_in : NICER_W;
         m.rows = (l == 0) ? TCF_K0 : NICER_W; m.K = NICER_W;
         m.hi = o; o += m.rows * m.K;
@@ -112,7 +101,7 @@ static TcfPlan plan_r(const nicer_sdf_net_t *net) {
         m.lo = o; o += m.rows * m.K;
     }
     MatSpec &f = pl.m[n];
-    f.layer = n; f.transposed = 1; f.layer0 = 0;
+    f.layer = n; f.transposed = 1; f.colmap = 0; f.col0 = 0;
     f.row0 = 1; f.w_rows = (int)net->d_out - 1; f.w_cols = NICER_W;
     f.rows = NICER_W; f.K = NICER_W;
     f.hi = o; o += f.rows * f.K;
@@ -151,91 +140,14 @@ __device__ void tcf_stage(const float *__restrict__ W, int row0, int w_rows, int
     }
 }
 
-struct Tile {
-    uint32_t tmem;        // TMEM address of the tile's column 0, lane 0
-    uint32_t lane_base;   // + this warp's lane quarter
-    uint64_t *bar;
-    uint32_t parity;
-    int id;               // named barrier id (1 or 2)
-    bool leader;
-};
-
-__device__ __forceinline__ void tile_sync(const Tile &t) { asm volatile("bar.sync %0, 128;" ::"r"(t.id) : "memory"); }
-
-// D[128 x N] = A[128 x K] * B^T:  A = (hi, lo) column ranges of the tile (TMEM), B = N rows x K, K-major in shared memory.
-// Split in issue / wait so that the caller can put the global loads its epilogue needs in flight while the MMAs run
-// (the tcgen05 asm statements are compiler barriers for memory operations: loads are not hoisted across them).
-__device__ __forceinline__ void gemm_issue(Tile &t, uint32_t whi, uint32_t wlo, int K, int N) {
-    tc::wait_st();
-    tc::fence_before_sync();
-    tile_sync(t);
-    if (t.leader) {
-        tc::fence_after_sync();
-        const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)N);
-        const uint32_t chunk = (uint32_t)N * 16u;
-        for (int ks = 0; ks < K / 8; ++ks) {
-            const uint64_t bhi = tc::smem_desc(whi + (uint32_t)ks * 2u * chunk, chunk, 128u);
-            const uint64_t blo = tc::smem_desc(wlo + (uint32_t)ks * 2u * chunk, chunk, 128u);
-            const uint32_t ahi = t.tmem + TCF_AHI + ks * 8, alo = t.tmem + TCF_ALO + ks * 8;
-            tc::mma_tf32_ts(t.tmem + TCF_D, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
-            tc::mma_tf32_ts(t.tmem + TCF_D, alo, bhi, idesc, 1u);
-            tc::mma_tf32_ts(t.tmem + TCF_D, ahi, blo, idesc, 1u);
-        }
-        tc::mma_commit(t.bar);
-    }
-}
-__device__ __forceinline__ void gemm_wait(Tile &t) {
-    tc::mbar_wait(t.bar, t.parity);
-    t.parity ^= 1u;
-    __syncwarp();
-    tc::fence_after_sync();
-}
-__device__ __forceinline__ void tile_gemm(Tile &t, uint32_t whi, uint32_t wlo, int K, int N) {
-    gemm_issue(t, whi, wlo, K, N);
-    gemm_wait(t);
-}
-
-__device__ __forceinline__ void ld_d8(const Tile &t, int c8, float v[8]) { tc::tmem_ld8(t.lane_base + TCF_D + c8 * 8, v); }
-__device__ __forceinline__ void st_a8(const Tile &t, int c8, const float v[8]) {
-    tc::tmem_st8_split(t.lane_base + TCF_AHI + c8 * 8, t.lane_base + TCF_ALO + c8 * 8, v);
-}
-
-// C (2, 4 or 8) consecutive A columns starting at a multiple of C, hi/lo split
-template <int C>
-__device__ __forceinline__ void st_a_small(const Tile &t, int col, const float v[C]) {
-    float h[C], l[C];
-#pragma unroll
-    for (int i = 0; i < C; ++i) { h[i] = tc::tf32_hi(v[i]); l[i] = v[i] - h[i]; }
-    const uint32_t ahi = t.lane_base + TCF_AHI + col, alo = t.lane_base + TCF_ALO + col;
-    if constexpr (C == 8) {
-        tc::tmem_st8(ahi, h);
-        tc::tmem_st8(alo, l);
-    } else if constexpr (C == 4) {
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ahi), "r"(__float_as_uint(h[0])),
-                     "r"(__float_as_uint(h[1])), "r"(__float_as_uint(h[2])), "r"(__float_as_uint(h[3])) : "memory");
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(alo), "r"(__float_as_uint(l[0])),
-                     "r"(__float_as_uint(l[1])), "r"(__float_as_uint(l[2])), "r"(__float_as_uint(l[3])) : "memory");
-    } else {
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(ahi), "r"(__float_as_uint(h[0])),
-                     "r"(__float_as_uint(h[1])) : "memory");
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(alo), "r"(__float_as_uint(l[0])),
-                     "r"(__float_as_uint(l[1])) : "memory");
-    }
-}
-
-struct TcfShared {
-    uint64_t bars[2];
-    uint32_t tmem_slot;
-};
-
 // common per-CTA setup: staged operands, biases, levels, barriers, TMEM. Returns the tile of the calling thread.
 __device__ __forceinline__ Tile tcf_setup(const nicer_sdf_net_t &net, const LevelScales &ls, const TcfPlan &pl, float *smem,
                                           TcfShared &sh, LevelInfo *&lv) {
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int n = (int)net.n_hidden, L = (int)net.grid.L;
     for (int i = 0; i < pl.n_mats; ++i) {
         const MatSpec &m = pl.m[i];
-        tcf_stage(net.W[m.layer], m.row0, m.w_rows, m.w_cols, m.rows, m.K, m.transposed != 0, m.layer0 != 0, smem + m.hi, smem + m.lo);
+        tcf_stage(net.W[m.layer], m.row0, m.w_rows, m.w_cols, m.rows, m.K, m.transposed != 0, m.colmap != 0, smem + m.hi, smem + m.lo);
     }
     const int nfeat = (int)net.d_out - 1;
     for (int l = 0; l <= n; ++l) {
@@ -246,21 +158,7 @@ __device__ __forceinline__ Tile tcf_setup(const nicer_sdf_net_t &net, const Leve
     for (int i = tid; i < NICER_W; i += TCF_THREADS) smem[pl.wl_sdf + i] = net.W[n][i];
     lv = reinterpret_cast<LevelInfo *>(smem + pl.lv);
     for (int l = tid; l < L; l += TCF_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
-    if (tid == 0) { tc::mbar_init(&sh.bars[0], 1); tc::mbar_init(&sh.bars[1], 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc(&sh.tmem_slot, TCF_TMEM);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    Tile t;
-    const int tile = tid >> 7;
-    t.tmem = sh.tmem_slot + (uint32_t)tile * TCF_TILE_COLS;
-    t.lane_base = t.tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    t.bar = &sh.bars[tile];
-    t.parity = 0;
-    t.id = 1 + tile;
-    t.leader = (tid & 127) == 0;
-    return t;
+    return tile_setup(sh, TCF_ALO, TCF_D);
 }
 
 __device__ __forceinline__ void mat_issue(Tile &t, const TcfPlan &pl, int i, float *smem) {
@@ -270,17 +168,6 @@ __device__ __forceinline__ void mat_gemm(Tile &t, const TcfPlan &pl, int i, floa
     mat_issue(t, pl, i, smem);
     gemm_wait(t);
 }
-// all 64 values of one saved layer row-block for this point (issued together: 64 loads in flight)
-__device__ __forceinline__ void load64(const float *__restrict__ base, size_t row0, size_t Ps, uint32_t p, float v[NICER_W]) {
-#pragma unroll
-    for (int j = 0; j < NICER_W; ++j) v[j] = __ldg(base + (row0 + j) * Ps + p);
-}
-// same through the coherent path (for a buffer the kernel also writes)
-__device__ __forceinline__ void load64_rw(const float *base, size_t row0, size_t Ps, uint32_t p, float v[NICER_W]) {
-#pragma unroll
-    for (int j = 0; j < NICER_W; ++j) v[j] = base[(row0 + j) * Ps + p];
-}
-
 template <int C>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 sdf_forward_tc_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
@@ -389,9 +276,7 @@ sdf_forward_tc_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
             }
         }
     }
-    tc::fence_before_sync();
-    __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
+    tile_teardown(sh);
 }
 
 // Kernel B: gradient chain  q_n = W_n[0,:] * sp'(z_n),  r_{l-1} = W_{l-1}^T q_l,  q_l = r_l * sp'(z_l),  g = J^T r_0
@@ -495,9 +380,7 @@ sdf_forward_tc_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
             }
         }
     }
-    tc::fence_before_sync();
-    __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
+    tile_teardown(sh);
 }
 
 int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
@@ -636,9 +519,7 @@ sdf_backward_tc_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
             if (l < n) mat_issue(t, pl, l, smem);   // u_{l+1} = W_l tan_l
         }
     }
-    tc::fence_before_sync();
-    __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
+    tile_teardown(sh);
 }
 
 // Kernel R: reverse pass.  abar_n = W_n^T [g_sdf, g_feat],  zbar_l = abar_l sp'(z_l) + ZB_l (second-order part from
@@ -756,18 +637,7 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
         for (int l = 0; l < 32 / C; ++l) {
             if (l < L) {
                 float gy2[C];
-                if constexpr (C == 8) {
-                    tc::tmem_ld8(t.lane_base + TCF_D + l * 8, gy2);
-                } else if constexpr (C == 4) {
-                    uint32_t r0, r1, r2, r3;
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(t.lane_base + TCF_D + l * 4) : "memory");
-                    gy2[0] = __uint_as_float(r0); gy2[1] = __uint_as_float(r1); gy2[2] = __uint_as_float(r2); gy2[3] = __uint_as_float(r3);
-                } else {
-                    uint32_t r0, r1;
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(t.lane_base + TCF_D + l * 2) : "memory");
-                    gy2[0] = __uint_as_float(r0); gy2[1] = __uint_as_float(r1);
-                }
+                ld_d_small<C>(t, l * C, gy2);
                 tc::wait_ld();
 #pragma unroll
                 for (int c = 0; c < C; ++c)
@@ -810,9 +680,7 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
             for (int d = 0; d < 3; ++d) grad_x[3 * (size_t)p + d] += xb[d] + xu[d] / 2.0f / df;
         }
     }
-    tc::fence_before_sync();
-    __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
+    tile_teardown(sh);
 }
 
 int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,

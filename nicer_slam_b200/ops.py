@@ -122,10 +122,15 @@ import os as _os
 _WGRAD_LIBRARY_MIN_P = 0 if _os.environ.get("NICER_WGRAD", "") == "cublas" else (1 << 62)
 
 
-def outer_accum(A, B, Cmat, bias=None):
-    """Cmat[M,N] += A[M,P] @ B[N,P]^T ; bias[M] += A.sum(1).  A, B feature-major (row stride = P)."""
+def outer_accum(A, B, Cmat, bias=None, col0=0):
+    """Cmat[M, col0:col0+N] += A[M,P] @ B[N,P]^T ; bias[M] += A.sum(1).  A, B feature-major (row stride = P)."""
     M, P = A.shape
     N = B.shape[0]
+    if col0:
+        cptr = C.c_void_p(_lib.require(Cmat, torch.float32, "C").data_ptr() + 4 * col0)
+        check(lib().nicer_outer_accum(ptr(A), A.stride(0), M, ptr(B), B.stride(0), N, P, cptr, Cmat.stride(0),
+                                      ptr(bias) if bias is not None else None, stream()), "nicer_outer_accum")
+        return
     if A.is_cuda and P >= _WGRAD_LIBRARY_MIN_P:
         Cmat.addmm_(A, B.t())
         if bias is not None:
@@ -273,7 +278,13 @@ class ColorNetFn(torch.autograd.Function):
             W = wb[2 * l]
             dW, db = torch.zeros_like(W), torch.zeros(W.shape[0], device=dev)
             if l == 0:
-                outer_accum(ZB[:HIDDEN], H0, dW, db)
+                # input = [x, PE(view), normals (33) | feat (F) | grid]: the feature block reads feat_fm in place, the
+                # kernels only materialise the 33 + L*C other rows of H0
+                nf = meta.feature
+                outer_accum(ZB[:HIDDEN], H0[:33], dW, db)
+                outer_accum(ZB[:HIDDEN], feat_fm, dW, None, col0=33)
+                if meta.d_in > 33 + nf:
+                    outer_accum(ZB[:HIDDEN], H0[33 + nf:], dW, None, col0=33 + nf)
             elif l < n:
                 outer_accum(ZB[l * HIDDEN:(l + 1) * HIDDEN], A_fm[(l - 1) * HIDDEN:l * HIDDEN], dW, db)
             else:
