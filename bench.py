@@ -335,7 +335,7 @@ def main():
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)   # 192 MiB > 126 MB L2
 
     graphed = None
-    if not args.no_graph:
+    if not args.no_graph and world == 1:    # N > 1 runs eagerly: the step contains NCCL collectives (voxel counter)
         from nicer_slam_b200.graph import GraphedStep
         graphed = GraphedStep(lambda: step.run(), warmup=3)     # forward + loss + backward as ONE CUDA graph
 
@@ -359,7 +359,7 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count
     eager_ms = None
-    if graphed is not None and rank == 0:
+    if graphed is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(2):
             step.run()
