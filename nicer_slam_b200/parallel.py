@@ -95,23 +95,36 @@ def gather_ground_truth(gt):
     return res
 
 
-def allreduce_gradients(model, extra=(), average=False):
-    """ONE all-reduce (sum) over a flat buffer of every parameter gradient (+ extra leaf tensors, e.g. the pose
-    7-vectors).  Parameters without a gradient contribute zeros so that all ranks reduce the same layout."""
+def allreduce_gradients(model, extra=(), average=False, big=1 << 20):
+    """Sum every parameter gradient (+ extra leaf tensors, e.g. the pose 7-vectors) over the ranks: the small ones
+    (MLP weights, poses) travel in ONE flat buffer, the grid gradients (>= `big` elements; the color grid is 1 GB) are
+    reduced in place without a staging copy.  Parameters without a gradient contribute zeros so that all ranks issue
+    the same collectives."""
     w = world()
     if w == 1:
         return
     tensors = [p for p in model.parameters() if p.requires_grad] + [t for t in extra if t is not None]
-    grads = [t.grad if t.grad is not None else torch.zeros_like(t) for t in tensors]
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    if average:
-        flat.div_(w)
-    off = 0
-    for t, g in zip(tensors, grads):
-        n = g.numel()
-        t.grad = flat[off:off + n].view_as(g)
-        off += n
+    small, small_g = [], []
+    for t in tensors:
+        if t.grad is None:
+            t.grad = torch.zeros_like(t)
+        if t.grad.numel() >= big and t.grad.is_contiguous():
+            dist.all_reduce(t.grad, op=dist.ReduceOp.SUM)
+            if average:
+                t.grad.div_(w)
+        else:
+            small.append(t)
+            small_g.append(t.grad)
+    if small:
+        flat = torch.cat([g.reshape(-1) for g in small_g])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if average:
+            flat.div_(w)
+        off = 0
+        for t, g in zip(small, small_g):
+            n = g.numel()
+            t.grad = flat[off:off + n].view_as(g)
+            off += n
 
 
 def all_reduce_sum_(t):
