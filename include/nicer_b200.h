@@ -90,6 +90,8 @@ typedef struct {
  *   Z    [n_hidden*64][P]   pre-activations z_l
  *   R    [(n_hidden-1)*64][P] adjoints r_l = d sdf / d a_l for l<n (r_n is W[n][0,:])   (may be NULL if n_hidden==1)
  *   DYDX [L*3*C][P]         d enc / d u   (K1's dy_dx, feature-major)
+ *   H0   [d_in][P]          the network input [x, PE(x), grid(x)] (operand of the layer-0 weight gradient, so that
+ *                           the backward pass never re-reads the grid)
  */
 #define NICER_SDF_ONLY 1u        /* sdf only: no feat, no gradient, nothing saved (sampler pass, get_sdf_vals) */
 #define NICER_SDF_ACCUMULATE 2u  /* add into sdf/feat/grad instead of overwriting (coarse+fine sum, base_networks.py:40) */
@@ -97,7 +99,7 @@ typedef struct {
 
 int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags,
                       float *sdf /*[P]*/, float *feat_fm /*[64][P]*/, float *grad /*[P,3]*/,
-                      float *Z, float *R, float *DYDX, void *stream);
+                      float *Z, float *R, float *DYDX, float *H0, void *stream);
 
 /* Backward of (sdf, feat, grad) w.r.t. x, the grid and (through the workspace below) the weights.
  *   g_sdf [P] | NULL, g_feat_fm [64][P] | NULL, g_grad [P,3] | NULL   upstream gradients
@@ -106,13 +108,13 @@ int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, ui
  *   Outputs for nicer_outer_accum (all fm, written):
  *     ZB  [n_hidden*64][P]  dL/dz_l          QB  [n_hidden*64][P]  q_l = r_l * softplus'(z_l)
  *     AB  [n_hidden*64][P]  a_l              TAN [n_hidden*64][P]  tangent of a_l in direction g_grad
- *     H0  [d_in][P]         network input    T0  [d_in][P]         tangent of the network input
+ *     T0  [d_in][P]         tangent of the network input (H0, the input itself, is saved by the forward)
  */
 int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P,
                        const float *Z, const float *R, const float *DYDX,
                        const float *g_sdf, const float *g_feat_fm, const float *g_grad,
                        float *grad_x, float *grad_table,
-                       float *ZB, float *QB, float *AB, float *TAN, float *H0, float *T0, void *stream);
+                       float *ZB, float *QB, float *AB, float *TAN, float *T0, void *stream);
 
 typedef struct {
     nicer_grid_t grid;         /* grid.table == NULL: no color grid (use_grid_feature=false) */
@@ -125,19 +127,21 @@ typedef struct {
 } nicer_color_net_t;
 
 /* rgb [P,3] = sigmoid(MLP([x, PE(view), normals, feat, grid(x)])).  A_fm [n_hidden*64][P] saved (post-ReLU).
- * DYDX [L*3*C][P] saved only when want_dx (x requires grad and grid not detached), else NULL. */
+ * DYDX [L*3*C][P] saved only when want_dx (x requires grad and grid not detached), else NULL.
+ * H0 [d_in][P] | NULL: the network input saved for the layer-0 weight gradient; only rows [0,33) (x, PE(view),
+ * normals) and [33+feature, d_in) (grid) are written -- rows [33,33+feature) are feat_fm itself. */
 int nicer_color_forward(const nicer_color_net_t *net, const float *x, const float *view /*[P,3]*/,
                         const float *normals /*[P,3]*/, const float *feat_fm /*[64][P]*/, uint32_t P,
-                        float *rgb, float *A_fm, float *DYDX, void *stream);
+                        float *rgb, float *A_fm, float *DYDX, float *H0, void *stream);
 
 /* g_rgb [P,3] upstream.  Outputs: grad_x (+=, NULL ok), grad_view [P,3] (written, NULL ok),
  * grad_normals [P,3] (written), grad_feat_fm [64][P] (written), grad_table (atomics, NULL when detached),
- * ZB [n_hidden*64][P] dL/dz_l, OB [3][P] dL/d(pre-sigmoid), H0 [d_in][P] network input (for nicer_outer_accum). */
+ * ZB [n_hidden*64][P] dL/dz_l, OB [3][P] dL/d(pre-sigmoid) (for nicer_outer_accum). */
 int nicer_color_backward(const nicer_color_net_t *net, const float *x, const float *view,
                          const float *normals, const float *feat_fm, uint32_t P, const float *rgb,
                          const float *A_fm, const float *DYDX, const float *g_rgb,
                          float *grad_x, float *grad_view, float *grad_normals, float *grad_feat_fm,
-                         float *grad_table, float *ZB, float *OB, float *H0, void *stream);
+                         float *grad_table, float *ZB, float *OB, void *stream);
 
 /* C[M,N] (row stride ldc) += A[M][P] * B[N][P]^T ;  bias[M] += rowsum(A) when bias != NULL.
  * A, B feature-major with row strides lda, ldb (>= P).  M <= 64, N <= 144. */

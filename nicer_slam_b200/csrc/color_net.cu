@@ -21,7 +21,7 @@ static ColorSmemLayout color_layout(int n_hidden) {
     s.WL = o; o += 4 * NICER_W;
     s.b0 = o; o += NICER_W;
     for (int i = 0; i < 3; ++i) { s.b[i] = o; if (i < n_hidden - 1) o += NICER_W; }
-    s.lv = o; o += NICER_MAX_LEVELS * 4;
+    s.lv = o; o += NICER_MAX_LEVELS * LEVEL_INFO_WORDS;
     s.col = o; o += NICER_W * COL_BLOCK;
     s.total_floats = o;
     return s;
@@ -69,7 +69,7 @@ template <int C>
 __global__ void __launch_bounds__(COL_BLOCK, 2)
 color_forward_kernel(const nicer_color_net_t net, const LevelScales ls, const ColorSmemLayout lay, const float *__restrict__ X,
                      const float *__restrict__ V, const float *__restrict__ N, const float *__restrict__ feat_fm,
-                     uint32_t P, float *rgb, float *A_fm, float *DYDX) {
+                     uint32_t P, float *rgb, float *A_fm, float *DYDX, float *H0) {
     extern __shared__ __align__(16) float smem[];
     ColorNetView nv;
     stage_color_net(net, ls, lay, smem, nv);
@@ -78,7 +78,7 @@ color_forward_kernel(const nicer_color_net_t net, const LevelScales ls, const Co
     const uint32_t tiles = (P + COL_BLOCK - 1) / COL_BLOCK;
     for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const uint32_t p = t * COL_BLOCK + threadIdx.x;
-        if (p < P) color_forward_sample<C>(nv, X, V, N, feat_fm, p, P, col, COL_BLOCK, rgb, A_fm, DYDX);
+        if (p < P) color_forward_sample<C>(nv, X, V, N, feat_fm, p, P, col, COL_BLOCK, rgb, A_fm, DYDX, H0);
     }
 }
 
@@ -88,7 +88,7 @@ color_backward_kernel(const nicer_color_net_t net, const LevelScales ls, const C
                       const float *__restrict__ V, const float *__restrict__ N, const float *__restrict__ feat_fm,
                       uint32_t P, const float *rgb, const float *A_fm, const float *DYDX, const float *g_rgb,
                       float *grad_x, float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table,
-                      float *ZB, float *OB, float *H0) {
+                      float *ZB, float *OB) {
     extern __shared__ __align__(16) float smem[];
     ColorNetView nv;
     stage_color_net(net, ls, lay, smem, nv);
@@ -99,7 +99,7 @@ color_backward_kernel(const nicer_color_net_t net, const LevelScales ls, const C
         const uint32_t p = t * COL_BLOCK + threadIdx.x;
         if (p < P)
             color_backward_sample<C>(nv, X, V, N, feat_fm, p, P, rgb, A_fm, DYDX, g_rgb, grad_x, grad_view, grad_normals,
-                                     grad_feat_fm, grad_table, ZB, OB, H0, col, COL_BLOCK);
+                                     grad_feat_fm, grad_table, ZB, OB, col, COL_BLOCK);
     }
 }
 
@@ -122,11 +122,11 @@ static int check_color_net(const nicer_color_net_t *net, const char *who) {
 }
 
 int launch_color_forward_tc(const nicer_color_net_t *net, const float *x, const float *view, const float *normals, const float *feat_fm,
-                            uint32_t P, float *rgb, float *A_fm, float *DYDX, cudaStream_t st);
+                            uint32_t P, float *rgb, float *A_fm, float *DYDX, float *H0, cudaStream_t st);
 int launch_color_backward_tc(const nicer_color_net_t *net, const float *x, const float *view, const float *normals, uint32_t P,
                              const float *rgb, const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
                              float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table, float *ZB, float *OB,
-                             float *H0, cudaStream_t st);
+                             cudaStream_t st);
 
 }  // namespace nicer
 
@@ -134,12 +134,12 @@ using namespace nicer;
 
 extern "C" int nicer_color_forward(const nicer_color_net_t *net, const float *x, const float *view,
                                    const float *normals, const float *feat_fm, uint32_t P, float *rgb, float *A_fm,
-                                   float *DYDX, void *stream) {
+                                   float *DYDX, float *H0, void *stream) {
     if (int e = check_color_net(net, "nicer_color_forward")) return e;
     if (P == 0) return 0;
     if (!x || !view || !normals || !feat_fm || !rgb || !A_fm) NICER_FAIL(-1, "nicer_color_forward: NULL pointer");
     {
-        const int r = launch_color_forward_tc(net, x, view, normals, feat_fm, P, rgb, A_fm, DYDX, (cudaStream_t)stream);
+        const int r = launch_color_forward_tc(net, x, view, normals, feat_fm, P, rgb, A_fm, DYDX, H0, (cudaStream_t)stream);
         if (r != 0) return r < 0 ? r : 0;
     }
     ColorSmemLayout lay = color_layout((int)net->n_hidden);
@@ -153,7 +153,7 @@ extern "C" int nicer_color_forward(const nicer_color_net_t *net, const float *x,
     do {                                                                                                             \
         NICER_CUDA(cudaFuncSetAttribute(color_forward_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
                    "nicer_color_forward");                                                                           \
-        color_forward_kernel<CC><<<grid, COL_BLOCK, smem, st>>>(*net, ls, lay, x, view, normals, feat_fm, P, rgb, A_fm, DYDX); \
+        color_forward_kernel<CC><<<grid, COL_BLOCK, smem, st>>>(*net, ls, lay, x, view, normals, feat_fm, P, rgb, A_fm, DYDX, H0); \
     } while (0)
     switch (C) {
         case 2: LAUNCH(2); break;
@@ -169,16 +169,16 @@ extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x
                                     const float *normals, const float *feat_fm, uint32_t P, const float *rgb,
                                     const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
                                     float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table,
-                                    float *ZB, float *OB, float *H0, void *stream) {
+                                    float *ZB, float *OB, void *stream) {
     if (int e = check_color_net(net, "nicer_color_backward")) return e;
     if (P == 0) return 0;
-    if (!x || !view || !normals || !feat_fm || !rgb || !A_fm || !g_rgb || !grad_normals || !grad_feat_fm || !ZB || !OB || !H0)
+    if (!x || !view || !normals || !feat_fm || !rgb || !A_fm || !g_rgb || !grad_normals || !grad_feat_fm || !ZB || !OB)
         NICER_FAIL(-1, "nicer_color_backward: NULL pointer");
     if (net->grid.table && !net->grid_detached && !grad_table)
         NICER_FAIL(-1, "nicer_color_backward: grad_table required when the grid is not detached");
     {
         const int r = launch_color_backward_tc(net, x, view, normals, P, rgb, A_fm, DYDX, g_rgb, grad_x, grad_view, grad_normals,
-                                               grad_feat_fm, grad_table, ZB, OB, H0, (cudaStream_t)stream);
+                                               grad_feat_fm, grad_table, ZB, OB, (cudaStream_t)stream);
         if (r != 0) return r < 0 ? r : 0;
     }
     ColorSmemLayout lay = color_layout((int)net->n_hidden);
@@ -194,7 +194,7 @@ extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x
                    "nicer_color_backward");                                                                           \
         color_backward_kernel<CC><<<grid, COL_BLOCK, smem, st>>>(*net, ls, lay, x, view, normals, feat_fm, P, rgb, A_fm, DYDX, \
                                                                   g_rgb, grad_x, grad_view, grad_normals, grad_feat_fm, \
-                                                                  grad_table, ZB, OB, H0);                            \
+                                                                  grad_table, ZB, OB);                                \
     } while (0)
     switch (C) {
         case 2: LAUNCH(2); break;

@@ -25,7 +25,7 @@ NHD float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 template <int C>
 NHD void color_forward_sample(const ColorNetView &nv, const float *X, const float *V, const float *N,
                               const float *feat_fm, uint32_t p, uint32_t P, float *col, int cs, float *rgb,
-                              float *A_fm, float *DYDX) {
+                              float *A_fm, float *DYDX, float *H0) {
     const size_t Ps = P;
     const int n = nv.n_hidden;
     float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
@@ -34,9 +34,11 @@ NHD void color_forward_sample(const ColorNetView &nv, const float *X, const floa
 #pragma unroll
     for (int j = 0; j < NICER_W; ++j) acc[j] = nv.b0[j];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) axpy64(acc, nv.W0t + d * NICER_W, x[d]);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) axpy64(acc, nv.W0t + (3 + d) * NICER_W, v[d]);
+    for (int d = 0; d < 3; ++d) {
+        axpy64(acc, nv.W0t + d * NICER_W, x[d]);
+        axpy64(acc, nv.W0t + (3 + d) * NICER_W, v[d]);
+        if (H0) { H0[(size_t)d * Ps + p] = x[d]; H0[(size_t)(3 + d) * Ps + p] = v[d]; }
+    }
     {
         float fr = 1.0f;
         for (int f = 0; f < nv.multires_view; ++f) {
@@ -44,14 +46,20 @@ NHD void color_forward_sample(const ColorNetView &nv, const float *X, const floa
             for (int d = 0; d < 3; ++d) {
                 float s, c;
                 sincosf(v[d] * fr, &s, &c);
-                axpy64(acc, nv.W0t + (6 + 6 * f + d) * NICER_W, s);
-                axpy64(acc, nv.W0t + (6 + 6 * f + 3 + d) * NICER_W, c);
+                const int ks = 6 + 6 * f + d, kc = ks + 3;
+                axpy64(acc, nv.W0t + ks * NICER_W, s);
+                axpy64(acc, nv.W0t + kc * NICER_W, c);
+                if (H0) { H0[(size_t)ks * Ps + p] = s; H0[(size_t)kc * Ps + p] = c; }
             }
             fr *= 2.0f;
         }
     }
 #pragma unroll
-    for (int d = 0; d < 3; ++d) axpy64(acc, nv.W0t + (nv.off_normal + d) * NICER_W, N[3 * (size_t)p + d]);
+    for (int d = 0; d < 3; ++d) {
+        const float nd = N[3 * (size_t)p + d];
+        axpy64(acc, nv.W0t + (nv.off_normal + d) * NICER_W, nd);
+        if (H0) H0[(size_t)(nv.off_normal + d) * Ps + p] = nd;
+    }
     for (int j = 0; j < nv.feature; ++j) axpy64(acc, nv.W0t + (nv.off_feat + j) * NICER_W, feat_fm[(size_t)j * Ps + p]);
     if (nv.table) {
         float u[3];
@@ -61,7 +69,10 @@ NHD void color_forward_sample(const ColorNetView &nv, const float *X, const floa
             if (DYDX) encode_level<C, true>(nv.table, nv.lv[l], u, feat, dfeat);
             else      encode_level<C, false>(nv.table, nv.lv[l], u, feat, dfeat);
 #pragma unroll
-            for (int c = 0; c < C; ++c) axpy64(acc, nv.W0t + (nv.off_grid + l * C + c) * NICER_W, feat[c]);
+            for (int c = 0; c < C; ++c) {
+                axpy64(acc, nv.W0t + (nv.off_grid + l * C + c) * NICER_W, feat[c]);
+                if (H0) H0[(size_t)(nv.off_grid + l * C + c) * Ps + p] = feat[c];
+            }
             if (DYDX) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d)
@@ -99,7 +110,7 @@ NHD void color_backward_sample(const ColorNetView &nv, const float *X, const flo
                                const float *feat_fm, uint32_t p, uint32_t P, const float *rgb, const float *A_fm,
                                const float *DYDX, const float *g_rgb, float *grad_x, float *grad_view,
                                float *grad_normals, float *grad_feat_fm, float *grad_table, float *ZB, float *OB,
-                               float *H0, float *col, int cs) {
+                               float *col, int cs) {
     const size_t Ps = P;
     const int n = nv.n_hidden;
     float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
@@ -138,13 +149,11 @@ NHD void color_backward_sample(const ColorNetView &nv, const float *X, const flo
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         xb[d] = dot64(nv.W0t + d * NICER_W, q);
-        H0[(size_t)d * Ps + p] = x[d];
     }
     float vb[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         vb[d] = dot64(nv.W0t + (3 + d) * NICER_W, q);
-        H0[(size_t)(3 + d) * Ps + p] = v[d];
     }
     {
         float fr = 1.0f;
@@ -156,8 +165,6 @@ NHD void color_backward_sample(const ColorNetView &nv, const float *X, const flo
                 const int ks = 6 + 6 * f + d, kc = ks + 3;
                 const float hs = dot64(nv.W0t + ks * NICER_W, q), hc = dot64(nv.W0t + kc * NICER_W, q);
                 vb[d] += fr * (c * hs - s * hc);
-                H0[(size_t)ks * Ps + p] = s;
-                H0[(size_t)kc * Ps + p] = c;
             }
             fr *= 2.0f;
         }
@@ -170,25 +177,22 @@ NHD void color_backward_sample(const ColorNetView &nv, const float *X, const flo
     for (int d = 0; d < 3; ++d) {
         const int k = nv.off_normal + d;
         grad_normals[3 * (size_t)p + d] = dot64(nv.W0t + k * NICER_W, q);
-        H0[(size_t)k * Ps + p] = N[3 * (size_t)p + d];
     }
     for (int j = 0; j < nv.feature; ++j) {
         const int k = nv.off_feat + j;
         grad_feat_fm[(size_t)j * Ps + p] = dot64(nv.W0t + k * NICER_W, q);
-        H0[(size_t)k * Ps + p] = feat_fm[(size_t)j * Ps + p];
     }
     float xu[3] = {0.f, 0.f, 0.f};
-    if (nv.table) {
+    if (nv.table && !nv.detached) {
         float u[3];
         to_unit(x, nv.df, u);
         for (int l = 0; l < nv.L; ++l) {
-            float gy[C], feat[C];
+            float gy[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int k = nv.off_grid + l * C + c;
-                gy[c] = nv.detached ? 0.f : dot64(nv.W0t + k * NICER_W, q);
-                feat[c] = 0.f;
-                if (DYDX && !nv.detached) {
+                gy[c] = dot64(nv.W0t + k * NICER_W, q);
+                if (DYDX) {
 #pragma unroll
                     for (int d = 0; d < 3; ++d) xu[d] += gy[c] * DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p];
                 }
@@ -202,18 +206,12 @@ NHD void color_backward_sample(const ColorNetView &nv, const float *X, const flo
                 corner_weights(cell, wt);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    float val[C], vv[C];
-                    load_entry<C>(nv.table, li, idx[k], val);
+                    float vv[C];
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        feat[c] += wt[k] * val[c];
-                        vv[c] = wt[k] * gy[c];
-                    }
-                    if (!nv.detached) scatter_entry<C>(grad_table, li, idx[k], vv);
+                    for (int c = 0; c < C; ++c) vv[c] = wt[k] * gy[c];
+                    scatter_entry<C>(grad_table, li, idx[k], vv);
                 }
             }
-#pragma unroll
-            for (int c = 0; c < C; ++c) H0[(size_t)(nv.off_grid + l * C + c) * Ps + p] = feat[c];
         }
     }
     if (grad_x) {

@@ -26,7 +26,7 @@ static ColorPlan color_plan_fwd() {
     const int sz[3] = {NICER_W * CT_KA, NICER_W * NICER_W, NICER_W * NICER_W};
     for (int i = 0; i < 3; ++i) { p.w_hi[i] = o; o += sz[i]; p.w_lo[i] = o; o += sz[i]; }
     p.b0 = o; o += NICER_W; p.b1 = o; o += NICER_W; p.wl = o; o += 4 * NICER_W;
-    p.lv = o; o += NICER_MAX_LEVELS * 4; p.total_floats = o;
+    p.lv = o; o += NICER_MAX_LEVELS * LEVEL_INFO_WORDS; p.total_floats = o;
     return p;
 }
 static ColorPlan color_plan_bwd() {
@@ -34,7 +34,7 @@ static ColorPlan color_plan_bwd() {
     const int sz[3] = {NICER_W * NICER_W, CT_NA * NICER_W, NICER_W * NICER_W};
     for (int i = 0; i < 3; ++i) { p.w_hi[i] = o; o += sz[i]; p.w_lo[i] = o; o += sz[i]; }
     p.b0 = o; o += NICER_W; p.b1 = o; o += NICER_W; p.wl = o; o += 4 * NICER_W;
-    p.lv = o; o += NICER_MAX_LEVELS * 4; p.total_floats = o;
+    p.lv = o; o += NICER_MAX_LEVELS * LEVEL_INFO_WORDS; p.total_floats = o;
     return p;
 }
 
@@ -63,20 +63,16 @@ __device__ __forceinline__ void ct_issue(Tile &t, const ColorPlan &pl, int i, in
 }
 
 // x (3), PE_4(view) (27), normals (3) -> 40 values (33 + zero padding), in the reference order
+template <bool DOUBLING>
 __device__ __forceinline__ void ct_xvn(const float x[3], const float v[3], const float nrm[3], float out[40]) {
     out[0] = x[0]; out[1] = x[1]; out[2] = x[2];
     out[3] = v[0]; out[4] = v[1]; out[5] = v[2];
-    float fr = 1.0f;
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
+    for (int d = 0; d < 3; ++d) {
+        float sc[8];
+        pe_sincos<4, DOUBLING>(v[d], sc);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            float s, c;
-            sincosf(v[d] * fr, &s, &c);
-            out[6 + 6 * f + d] = s;
-            out[6 + 6 * f + 3 + d] = c;
-        }
-        fr *= 2.0f;
+        for (int f = 0; f < 4; ++f) { out[6 + 6 * f + d] = sc[2 * f]; out[6 + 6 * f + 3 + d] = sc[2 * f + 1]; }
     }
     out[30] = nrm[0]; out[31] = nrm[1]; out[32] = nrm[2];
 #pragma unroll
@@ -87,7 +83,7 @@ template <int C>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 color_forward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, const ColorPlan pl, const float *__restrict__ X,
                         const float *__restrict__ V, const float *__restrict__ Nrm, const float *__restrict__ feat_fm, uint32_t P,
-                        float *rgb, float *A_fm, float *DYDX) {
+                        float *rgb, float *A_fm, float *DYDX, float *H0) {
     extern __shared__ __align__(16) float smem[];
     __shared__ TcfShared sh;
     const int tid = threadIdx.x;
@@ -120,9 +116,13 @@ color_forward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, const
             const float v[3] = {__ldg(V + 3 * (size_t)p), __ldg(V + 3 * (size_t)p + 1), __ldg(V + 3 * (size_t)p + 2)};
             const float nr[3] = {__ldg(Nrm + 3 * (size_t)p), __ldg(Nrm + 3 * (size_t)p + 1), __ldg(Nrm + 3 * (size_t)p + 2)};
             float xvn[40];
-            ct_xvn(x, v, nr, xvn);
+            ct_xvn<false>(x, v, nr, xvn);
 #pragma unroll
             for (int c8 = 0; c8 < 5; ++c8) st_a8(t, 4 + c8, &xvn[c8 * 8]);     // columns 32..71
+            if (H0 && valid) {
+#pragma unroll
+                for (int k = 0; k < 33; ++k) H0[(size_t)k * Ps + p] = xvn[k];  // rows 0..32 of the input (for dW0)
+            }
         }
         {
             float u[3];
@@ -141,6 +141,10 @@ color_forward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, const
                         }
                     } else {
                         encode_level<C, false>(net.grid.table, lv[l], u, feat, dfeat);
+                    }
+                    if (H0 && valid) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) H0[(size_t)(97 + l * C + c) * Ps + p] = feat[c];
                     }
                 } else {
 #pragma unroll
@@ -200,7 +204,7 @@ color_backward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, cons
                          const float *__restrict__ V, const float *__restrict__ Nrm, uint32_t P, const float *__restrict__ rgb,
                          const float *__restrict__ A_fm, const float *__restrict__ DYDX, const float *__restrict__ g_rgb,
                          float *grad_x, float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table, float *ZB,
-                         float *OB, float *H0) {
+                         float *OB) {
     extern __shared__ __align__(16) float smem[];
     __shared__ TcfShared sh;
     const int tid = threadIdx.x;
@@ -291,7 +295,7 @@ color_backward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, cons
             xb[0] = hp[0]; xb[1] = hp[1]; xb[2] = hp[2];
             float vb[3] = {hp[3], hp[4], hp[5]};
             float xvn[40];
-            ct_xvn(x, v3, nr, xvn);
+            ct_xvn<true>(x, v3, nr, xvn);
             float fr = 1.0f;
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
@@ -309,27 +313,21 @@ color_backward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, cons
                 }
 #pragma unroll
                 for (int d = 0; d < 3; ++d) grad_normals[3 * (size_t)p + d] = hp[30 + d];
-#pragma unroll
-                for (int k = 0; k < 33; ++k) H0[(size_t)k * Ps + p] = xvn[k];     // rows 0..32 of the input (for dW0)
             }
         }
         ct_issue(t, pl, 2, NICER_W, NICER_W, smem);        // hbar block b (features) = W0b^T zbar_1; A still holds zbar_1
-        // grid: scatter + dL/dx through the grid + grid rows of H0 while the MMAs run
+        // grid: scatter + dL/dx through the grid while the MMAs run (indices and weights only, no table reads)
         float xu[3] = {0.f, 0.f, 0.f};
-        if (has_grid) {
+        if (has_grid && !detached) {
             float u[3];
             to_unit(x, df, u);
 #pragma unroll
             for (int l = 0; l < 32 / C; ++l) {
                 if (l < L) {
-                    float feat[C];
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        feat[c] = 0.f;
-                        if (detached) gy[l * C + c] = 0.f;
+                    for (int c = 0; c < C; ++c)
 #pragma unroll
                         for (int d = 0; d < 3; ++d) xu[d] += gy[l * C + c] * dyv[(l * 3 + d) * C + c];
-                    }
                     const LevelInfo li = lv[l];
                     Cell3 cell = locate3(li, u);
                     if (cell.inside && valid) {
@@ -339,16 +337,11 @@ color_backward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, cons
                         corner_weights(cell, wt);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            float val[C], vv[C];
-                            load_entry<C>(net.grid.table, li, idx[k], val);
+                            float vv[C];
 #pragma unroll
-                            for (int c = 0; c < C; ++c) { feat[c] += wt[k] * val[c]; vv[c] = wt[k] * gy[l * C + c]; }
-                            if (!detached) scatter_entry<C>(grad_table, li, idx[k], vv);
+                            for (int c = 0; c < C; ++c) vv[c] = wt[k] * gy[l * C + c];
+                            scatter_entry<C>(grad_table, li, idx[k], vv);
                         }
-                    }
-                    if (valid) {
-#pragma unroll
-                        for (int c = 0; c < C; ++c) H0[(size_t)(97 + l * C + c) * Ps + p] = feat[c];
                     }
                 }
             }
@@ -376,7 +369,7 @@ bool tc_enabled();
 
 // 1: launched, 0: configuration not covered (caller falls back to the SIMT kernel), < 0: error
 int launch_color_forward_tc(const nicer_color_net_t *net, const float *x, const float *view, const float *normals, const float *feat_fm,
-                            uint32_t P, float *rgb, float *A_fm, float *DYDX, cudaStream_t st) {
+                            uint32_t P, float *rgb, float *A_fm, float *DYDX, float *H0, cudaStream_t st) {
     if (!tc_enabled() || net->n_hidden != 2 || net->multires_view != 4 || net->feature != 64) return 0;
     const bool has_grid = net->grid.table != nullptr;
     const LevelScales ls = host_level_scales(has_grid ? net->grid.L : 0, net->grid.S, net->grid.H);
@@ -388,7 +381,7 @@ int launch_color_forward_tc(const nicer_color_net_t *net, const float *x, const 
     do {                                                                                                                  \
         NICER_CUDA(cudaFuncSetAttribute(color_forward_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
                    "nicer_color_forward(tc)");                                                                            \
-        color_forward_tc_kernel<CC><<<grid, TCF_THREADS, smem, st>>>(*net, ls, pl, x, view, normals, feat_fm, P, rgb, A_fm, DYDX); \
+        color_forward_tc_kernel<CC><<<grid, TCF_THREADS, smem, st>>>(*net, ls, pl, x, view, normals, feat_fm, P, rgb, A_fm, DYDX, H0); \
     } while (0)
     switch (has_grid ? net->grid.C : 2) {
         case 2: LAUNCH(2); break;
@@ -403,7 +396,7 @@ int launch_color_forward_tc(const nicer_color_net_t *net, const float *x, const 
 int launch_color_backward_tc(const nicer_color_net_t *net, const float *x, const float *view, const float *normals, uint32_t P,
                              const float *rgb, const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
                              float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table, float *ZB, float *OB,
-                             float *H0, cudaStream_t st) {
+                             cudaStream_t st) {
     if (!tc_enabled() || net->n_hidden != 2 || net->multires_view != 4 || net->feature != 64) return 0;
     const bool has_grid = net->grid.table != nullptr;
     const LevelScales ls = host_level_scales(has_grid ? net->grid.L : 0, net->grid.S, net->grid.H);
@@ -416,7 +409,7 @@ int launch_color_backward_tc(const nicer_color_net_t *net, const float *x, const
         NICER_CUDA(cudaFuncSetAttribute(color_backward_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
                    "nicer_color_backward(tc)");                                                                            \
         color_backward_tc_kernel<CC><<<grid, TCF_THREADS, smem, st>>>(*net, ls, pl, x, view, normals, P, rgb, A_fm, DYDX, g_rgb, \
-                                                                      grad_x, grad_view, grad_normals, grad_feat_fm, grad_table, ZB, OB, H0); \
+                                                                      grad_x, grad_view, grad_normals, grad_feat_fm, grad_table, ZB, OB); \
     } while (0)
     switch (has_grid ? net->grid.C : 2) {
         case 2: LAUNCH(2); break;

@@ -107,13 +107,47 @@ NHD float fmul_exact(float a, float b) {
 NHD float sstep(float v) { return v * v * (3.0f - 2.0f * v); }
 NHD float sstep_d(float v) { return 6.0f * v * (1.0f - v); }
 
+// NeRF positional encoding of one coordinate: sc[2f] = sin(2^f x), sc[2f+1] = cos(2^f x), f < F (model/embedder.py).
+// DOUBLING (device, backward kernels only): sincosf at every STEP-th frequency, the ones between by angle doubling
+// (<= 2 doublings, abs error < 5e-7).  The forward kernels keep one sincosf per frequency: rendered depths feed the
+// discontinuous validity masks of the warp loss, where a last-bit difference can move a pixel across a mask edge.
+template <int F, bool DOUBLING = false>
+NHD void pe_sincos(float x, float *sc) {
+#if defined(__CUDA_ARCH__)
+    constexpr int STEP = DOUBLING ? ((F % 3 == 0) ? 3 : 2) : 1;
+    float s = 0.f, c = 1.f, fr = 1.0f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        if (f % STEP == 0) {
+            sincosf(x * fr, &s, &c);
+        } else {
+            const float s2 = 2.0f * s * c, c2 = fmaf(-2.0f * s, s, 1.0f);
+            s = s2; c = c2;
+        }
+        sc[2 * f] = s; sc[2 * f + 1] = c;
+        fr *= 2.0f;
+    }
+#else
+    float fr = 1.0f;
+    for (int f = 0; f < F; ++f) {
+        sincosf(x * fr, &sc[2 * f], &sc[2 * f + 1]);
+        fr *= 2.0f;
+    }
+#endif
+}
+
 // ------------------------------------------------------------------ grid geometry
 struct LevelInfo {
     uint32_t offset;        // first entry of the level
     uint32_t hashmap_size;  // entries in the level
     uint32_t resolution;    // ceil(scale) + 1
     float scale;            // exp2f(level*S)*H - 1
+    uint32_t dense;         // 1: p0 + res*(p1 + res*p2), 0: XOR hash   (decided per level, see level_is_dense)
+    uint32_t mode;          // how index % hashmap_size is taken: LEVEL_MOD_MASK / _WRAP / _GENERAL (make_level)
+    uint32_t mask;          // LEVEL_MOD_MASK: index % hashmap_size == index & mask for every index the level can produce
 };
+constexpr uint32_t LEVEL_MOD_GENERAL = 0u, LEVEL_MOD_MASK = 1u, LEVEL_MOD_WRAP = 2u;
+constexpr int LEVEL_INFO_WORDS = sizeof(LevelInfo) / 4;
 
 // Per-level scales exp2f(level*S)*H - 1 are evaluated on the HOST (common.cuh: host_level_scales) in the same fp32
 // steps as the reference (hashencoder.cu:180) and handed to the kernels by value: CUDA's exp2f (2 ulp) and glibc's
@@ -127,12 +161,28 @@ inline LevelScales host_level_scales(uint32_t L, float S, uint32_t H) {
     return ls;
 }
 
+NHD bool level_is_dense(const LevelInfo &li);
+
 NHD LevelInfo make_level(const int32_t *offsets, uint32_t level, float scale) {
     LevelInfo li;
     li.offset = (uint32_t)offsets[level];
     li.hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
     li.scale = scale;
     li.resolution = (uint32_t)ceilf(li.scale) + 1u;
+    li.dense = level_is_dense(li) ? 1u : 0u;
+    // The reference reduces every index modulo hashmap_size (hashencoder.cu:72).  Power-of-two levels (all hashed levels
+    // of the reference's configurations) take a mask.  For a dense level the largest vertex coordinate is
+    // floor(scale) + 1 (u <= 1), so the largest index is known: below hashmap_size the modulo is the identity (mask of
+    // all ones), below 2*hashmap_size (integer scales, where u == 1 reaches coordinate `resolution`) it is one
+    // conditional subtraction; anything else keeps the general modulo.
+    const uint32_t hs = li.hashmap_size;
+    const unsigned long long r = li.resolution, pmax = (unsigned long long)floorf(li.scale) + 1ull;
+    const unsigned long long max_index = pmax * (1ull + r + r * r);
+    li.mask = 0u;
+    if (hs != 0u && (hs & (hs - 1u)) == 0u) { li.mode = LEVEL_MOD_MASK; li.mask = hs - 1u; }
+    else if (li.dense && max_index < (unsigned long long)hs) { li.mode = LEVEL_MOD_MASK; li.mask = 0xffffffffu; }
+    else if (li.dense && max_index < 2ull * hs) li.mode = LEVEL_MOD_WRAP;
+    else li.mode = LEVEL_MOD_GENERAL;
     return li;
 }
 
@@ -150,10 +200,8 @@ NHD bool level_is_dense(const LevelInfo &li) {
 
 // entry index (not multiplied by C) of grid vertex p within a level
 NHD uint32_t vertex_index3(const LevelInfo &li, bool dense, uint32_t px, uint32_t py, uint32_t pz) {
-    const uint32_t hs = li.hashmap_size, res = li.resolution;
-    uint32_t index = dense ? px + res * (py + res * pz) : ((px * 1u) ^ (py * 2654435761u) ^ (pz * 805459861u));
-    if ((hs & (hs - 1u)) == 0u) return index & (hs - 1u);
-    return index >= hs ? index % hs : index;
+    const uint32_t res = li.resolution;
+    return dense ? px + res * (py + res * pz) : ((px * 1u) ^ (py * 2654435761u) ^ (pz * 805459861u));
 }
 
 // Interpolation cell of a point u in [0,1]^3 at one level.
@@ -182,10 +230,21 @@ NHD Cell3 locate3(const LevelInfo &li, const float u[3]) {
 }
 
 NHD void corner_indices(const LevelInfo &li, const Cell3 &c, uint32_t idx[8]) {
-    const bool dense = level_is_dense(li);
+    const bool dense = li.dense != 0u;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         idx[k] = vertex_index3(li, dense, c.pg[0] + (k & 1), c.pg[1] + ((k >> 1) & 1), c.pg[2] + ((k >> 2) & 1));
+    const uint32_t hs = li.hashmap_size;
+    if (li.mode == LEVEL_MOD_MASK) {       // level-uniform branches
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idx[k] &= li.mask;
+    } else if (li.mode == LEVEL_MOD_WRAP) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idx[k] = idx[k] >= hs ? idx[k] - hs : idx[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idx[k] = idx[k] >= hs ? idx[k] % hs : idx[k];
+    }
 }
 
 // trilinear weights in the reference's corner order (bit d of k selects the upper vertex in dim d)

@@ -29,7 +29,7 @@ static SdfSmemLayout sdf_layout(int n_hidden) {
     s.b0 = o; o += NICER_W;
     for (int i = 0; i < 3; ++i) { s.b[i] = o; if (i < n_hidden - 1) o += NICER_W; }
     s.bl_feat = o; o += NICER_W;
-    s.lv = o; o += NICER_MAX_LEVELS * 4;
+    s.lv = o; o += NICER_MAX_LEVELS * LEVEL_INFO_WORDS;
     s.col = o; o += COL_ROWS * SDF_CS;
     s.total_floats = o;
     return s;
@@ -86,7 +86,7 @@ __device__ void stage_sdf_net(const nicer_sdf_net_t &net, const LevelScales &ls,
 template <int C>
 __global__ void __launch_bounds__(SDF_BLOCK, 2)
 sdf_forward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSmemLayout lay, const float *__restrict__ X, uint32_t P,
-                   uint32_t flags, float *sdf, float *feat_fm, float *grad, float *Z, float *R, float *DYDX) {
+                   uint32_t flags, float *sdf, float *feat_fm, float *grad, float *Z, float *R, float *DYDX, float *H0) {
     extern __shared__ __align__(16) float smem[];
     SdfNetView nv;
     stage_sdf_net(net, ls, lay, smem, nv);
@@ -95,7 +95,7 @@ sdf_forward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSme
     const uint32_t tiles = (P + SDF_BLOCK - 1) / SDF_BLOCK;
     for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const uint32_t p = t * SDF_BLOCK + threadIdx.x;
-        if (p < P) sdf_forward_sample<C>(nv, X, p, P, flags, col, SDF_CS, sdf, feat_fm, grad, Z, R, DYDX);
+        if (p < P) sdf_forward_sample<C>(nv, X, p, P, flags, col, SDF_CS, sdf, feat_fm, grad, Z, R, DYDX, H0);
     }
 }
 
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(SDF_BLOCK, 2)
 sdf_backward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSmemLayout lay, const float *__restrict__ X, uint32_t P,
                     const float *Z, const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
                     const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB, float *AB,
-                    float *TAN, float *H0, float *T0) {
+                    float *TAN, float *T0) {
     extern __shared__ __align__(16) float smem[];
     SdfNetView nv;
     stage_sdf_net(net, ls, lay, smem, nv);
@@ -115,7 +115,7 @@ sdf_backward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSm
         const uint32_t p = t * SDF_BLOCK + threadIdx.x;
         if (p < P)
             sdf_backward_sample<C>(nv, X, p, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB,
-                                   TAN, H0, T0, col, SDF_CS);
+                                   TAN, T0, col, SDF_CS);
     }
 }
 
@@ -138,11 +138,11 @@ static int check_sdf_net(const nicer_sdf_net_t *net, const char *who) {
 bool tc_enabled();
 int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, cudaStream_t st);
 int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
-                          float *grad, float *Z, float *R, float *DYDX, cudaStream_t st);
+                          float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st);
 
 int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
                            const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
-                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *H0, float *T0, cudaStream_t st);
+                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st);
 
 template <typename K>
 static int prep_kernel(K kernel, size_t smem_bytes, const char *who) {
@@ -155,7 +155,7 @@ static int prep_kernel(K kernel, size_t smem_bytes, const char *who) {
 using namespace nicer;
 
 extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf,
-                                 float *feat_fm, float *grad, float *Z, float *R, float *DYDX, void *stream) {
+                                 float *feat_fm, float *grad, float *Z, float *R, float *DYDX, float *H0, void *stream) {
     if (int e = check_sdf_net(net, "nicer_sdf_forward")) return e;
     if (P == 0) return 0;
     if (!x || !sdf) NICER_FAIL(-1, "nicer_sdf_forward: x/sdf is NULL");
@@ -170,7 +170,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
     if (sdf_only && tc_enabled() && net->multires == 6)
         return launch_sdf_only_tc(net, x, P, flags, sdf, (cudaStream_t)stream);
     if (!sdf_only && tc_enabled() && net->multires == 6)
-        return launch_sdf_forward_tc(net, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX, (cudaStream_t)stream);
+        return launch_sdf_forward_tc(net, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX, H0, (cudaStream_t)stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);
@@ -180,7 +180,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
 #define LAUNCH(CC)                                                                                            \
     do {                                                                                                      \
         if (int e = prep_kernel(sdf_forward_kernel<CC>, smem, "nicer_sdf_forward")) return e;                 \
-        sdf_forward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, ls, lay, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX); \
+        sdf_forward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, ls, lay, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX, H0); \
     } while (0)
     switch (net->grid.C) {
         case 2: LAUNCH(2); break;
@@ -195,15 +195,15 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
 extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
                                   const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
                                   const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
-                                  float *AB, float *TAN, float *H0, float *T0, void *stream) {
+                                  float *AB, float *TAN, float *T0, void *stream) {
     if (int e = check_sdf_net(net, "nicer_sdf_backward")) return e;
     if (P == 0) return 0;
-    if (!x || !Z || !DYDX || !grad_table || !ZB || !QB || !AB || !TAN || !H0 || !T0)
+    if (!x || !Z || !DYDX || !grad_table || !ZB || !QB || !AB || !TAN || !T0)
         NICER_FAIL(-1, "nicer_sdf_backward: a required pointer is NULL");
     if (net->n_hidden > 1 && !R) NICER_FAIL(-1, "nicer_sdf_backward: R required for n_hidden > 1");
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_backward: n_hidden > 3 not built");
     if (tc_enabled() && net->multires == 6)
-        return launch_sdf_backward_tc(net, x, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB, TAN, H0, T0,
+        return launch_sdf_backward_tc(net, x, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB, TAN, T0,
                                       (cudaStream_t)stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
@@ -215,7 +215,7 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
     do {                                                                                                        \
         if (int e = prep_kernel(sdf_backward_kernel<CC>, smem, "nicer_sdf_backward")) return e;                 \
         sdf_backward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, ls, lay, x, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, \
-                                                               grad_x, grad_table, ZB, QB, AB, TAN, H0, T0);    \
+                                                               grad_x, grad_table, ZB, QB, AB, TAN, T0);        \
     } while (0)
     switch (net->grid.C) {
         case 2: LAUNCH(2); break;

@@ -71,7 +71,7 @@ NHD void to_unit(const float x[3], float df, float u[3]) {
 template <int C>
 NHD void sdf_forward_sample(const SdfNetView &nv, const float *X, uint32_t p, uint32_t P, uint32_t flags,
                             float *col, int cs, float *sdf, float *feat_fm, float *grad, float *Z, float *R,
-                            float *DYDX) {
+                            float *DYDX, float *H0) {
     const size_t Ps = P;
     const int n = nv.n_hidden;
     const bool sdf_only = (flags & F_SDF_ONLY) != 0;
@@ -85,7 +85,10 @@ NHD void sdf_forward_sample(const SdfNetView &nv, const float *X, uint32_t p, ui
     for (int j = 0; j < NICER_W; ++j) acc[j] = nv.b0[j];
     // ---- layer 0, input generated on the fly
 #pragma unroll
-    for (int d = 0; d < 3; ++d) axpy64(acc, nv.W0t + d * NICER_W, x[d]);
+    for (int d = 0; d < 3; ++d) {
+        axpy64(acc, nv.W0t + d * NICER_W, x[d]);
+        if (H0) H0[(size_t)d * Ps + p] = x[d];
+    }
     {
         float fr = 1.0f;
         for (int f = 0; f < nv.multires; ++f) {
@@ -93,8 +96,10 @@ NHD void sdf_forward_sample(const SdfNetView &nv, const float *X, uint32_t p, ui
             for (int d = 0; d < 3; ++d) {
                 float s, c;
                 sincosf(x[d] * fr, &s, &c);
-                axpy64(acc, nv.W0t + (3 + 6 * f + d) * NICER_W, s);
-                axpy64(acc, nv.W0t + (3 + 6 * f + 3 + d) * NICER_W, c);
+                const int ks = 3 + 6 * f + d, kc = ks + 3;
+                axpy64(acc, nv.W0t + ks * NICER_W, s);
+                axpy64(acc, nv.W0t + kc * NICER_W, c);
+                if (H0) { H0[(size_t)ks * Ps + p] = s; H0[(size_t)kc * Ps + p] = c; }
             }
             fr *= 2.0f;
         }
@@ -104,7 +109,10 @@ NHD void sdf_forward_sample(const SdfNetView &nv, const float *X, uint32_t p, ui
         if (sdf_only) encode_level<C, false>(nv.table, nv.lv[l], u, feat, dfeat);
         else          encode_level<C, true>(nv.table, nv.lv[l], u, feat, dfeat);
 #pragma unroll
-        for (int c = 0; c < C; ++c) axpy64(acc, nv.W0t + (nv.d_pe + l * C + c) * NICER_W, feat[c]);
+        for (int c = 0; c < C; ++c) {
+            axpy64(acc, nv.W0t + (nv.d_pe + l * C + c) * NICER_W, feat[c]);
+            if (H0) H0[(size_t)(nv.d_pe + l * C + c) * Ps + p] = feat[c];
+        }
         if (!sdf_only) {
 #pragma unroll
             for (int d = 0; d < 3; ++d)
@@ -196,7 +204,7 @@ template <int C>
 NHD void sdf_backward_sample(const SdfNetView &nv, const float *X, uint32_t p, uint32_t P, const float *Z,
                              const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
                              const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
-                             float *AB, float *TAN, float *H0, float *T0, float *col, int cs) {
+                             float *AB, float *TAN, float *T0, float *col, int cs) {
     const size_t Ps = P;
     const int n = nv.n_hidden;
     float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
@@ -216,7 +224,6 @@ NHD void sdf_backward_sample(const SdfNetView &nv, const float *X, uint32_t p, u
     for (int d = 0; d < 3; ++d) {
         axpy64(acc, nv.W0t + d * NICER_W, gg[d]);
         T0[(size_t)d * Ps + p] = gg[d];
-        H0[(size_t)d * Ps + p] = x[d];
     }
     {
         float fr = 1.0f;
@@ -229,8 +236,8 @@ NHD void sdf_backward_sample(const SdfNetView &nv, const float *X, uint32_t p, u
                 const float ts = fr * c * gg[d], tc = -fr * s * gg[d];
                 axpy64(acc, nv.W0t + ks * NICER_W, ts);
                 axpy64(acc, nv.W0t + kc * NICER_W, tc);
-                T0[(size_t)ks * Ps + p] = ts; H0[(size_t)ks * Ps + p] = s;
-                T0[(size_t)kc * Ps + p] = tc; H0[(size_t)kc * Ps + p] = c;
+                T0[(size_t)ks * Ps + p] = ts;
+                T0[(size_t)kc * Ps + p] = tc;
             }
             fr *= 2.0f;
         }
@@ -329,9 +336,6 @@ NHD void sdf_backward_sample(const SdfNetView &nv, const float *X, uint32_t p, u
         }
         const LevelInfo li = nv.lv[l];
         Cell3 cell = locate3(li, u);
-        float feat[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) feat[c] = 0.f;
         if (cell.inside) {
             uint32_t idx[8];
             corner_indices(li, cell, idx);
@@ -342,19 +346,13 @@ NHD void sdf_backward_sample(const SdfNetView &nv, const float *X, uint32_t p, u
             corner_dweights(cell, 2, dw2);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                float val[C], v[C];
-                load_entry<C>(nv.table, li, idx[k], val);
+                float v[C];
                 const float w2 = dw0[k] * ggu[0] + dw1[k] * ggu[1] + dw2[k] * ggu[2];
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    feat[c] += wt[k] * val[c];
-                    v[c] = wt[k] * gy1[c] + w2 * gy2[c];
-                }
+                for (int c = 0; c < C; ++c) v[c] = wt[k] * gy1[c] + w2 * gy2[c];
                 scatter_entry<C>(grad_table, li, idx[k], v);
             }
         }
-#pragma unroll
-        for (int c = 0; c < C; ++c) H0[(size_t)(nv.d_pe + l * C + c) * Ps + p] = feat[c];
     }
     if (grad_x) {
 #pragma unroll

@@ -36,7 +36,7 @@ static TcSmemLayout tc_layout(int n_hidden) {
         s.bias[l] = o; if (l < n_hidden) o += NICER_W;
     }
     s.wl_sdf = o; o += NICER_W;
-    s.lv = o; o += NICER_MAX_LEVELS * 4;
+    s.lv = o; o += NICER_MAX_LEVELS * LEVEL_INFO_WORDS;
     s.total_floats = o;
     return s;
 }

@@ -45,7 +45,7 @@ static TcfPlan plan_a(const nicer_sdf_net_t *net) {
     }
     for (int l = n + 1; l < 5; ++l) pl.bias[l] = -1;
     pl.wl_sdf = o; o += NICER_W;
-    pl.lv = o; o += NICER_MAX_LEVELS * 4;
+    pl.lv = o; o += NICER_MAX_LEVELS * LEVEL_INFO_WORDS;
     pl.total_floats = o;
     return pl;
 }
@@ -66,7 +66,7 @@ static TcfPlan plan_b(const nicer_sdf_net_t *net) {
     }
     for (int l = 0; l < 5; ++l) pl.bias[l] = -1;
     pl.wl_sdf = o; o += NICER_W;
-    pl.lv = o; o += NICER_MAX_LEVELS * 4;
+    pl.lv = o; o += NICER_MAX_LEVELS * LEVEL_INFO_WORDS;
     pl.total_floats = o;
     return pl;
 }
@@ -85,7 +85,7 @@ static TcfPlan plan_t(const nicer_sdf_net_t *net) {
     }
     for (int l = 0; l < 5; ++l) pl.bias[l] = -1;
     pl.wl_sdf = o; o += NICER_W;
-    pl.lv = o; o += NICER_MAX_LEVELS * 4;
+    pl.lv = o; o += NICER_MAX_LEVELS * LEVEL_INFO_WORDS;
     pl.total_floats = o;
     return pl;
 }
@@ -108,7 +108,7 @@ static TcfPlan plan_r(const nicer_sdf_net_t *net) {
     f.lo = o; o += f.rows * f.K;
     pl.n_mats = n + 1;
     pl.wl_sdf = o; o += NICER_W;
-    pl.lv = o; o += NICER_MAX_LEVELS * 4;
+    pl.lv = o; o += NICER_MAX_LEVELS * LEVEL_INFO_WORDS;
     pl.total_floats = o;
     return pl;
 }
@@ -171,7 +171,7 @@ __device__ __forceinline__ void mat_gemm(Tile &t, const TcfPlan &pl, int i, floa
 template <int C>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 sdf_forward_tc_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
-                      uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z, float *DYDX) {
+                      uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z, float *DYDX, float *H0) {
     extern __shared__ __align__(16) float smem[];
     __shared__ TcfShared sh;
     LevelInfo *lv;
@@ -197,22 +197,21 @@ sdf_forward_tc_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
         {
             float pe[48];
             pe[0] = x[0]; pe[1] = x[1]; pe[2] = x[2];
-            float fr = 1.0f;
 #pragma unroll
-            for (int f = 0; f < 6; ++f) {
+            for (int d = 0; d < 3; ++d) {
+                float sc[12];
+                pe_sincos<6>(x[d], sc);
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    float s, c;
-                    sincosf(x[d] * fr, &s, &c);
-                    pe[3 + 6 * f + d] = s;
-                    pe[3 + 6 * f + 3 + d] = c;
-                }
-                fr *= 2.0f;
+                for (int f = 0; f < 6; ++f) { pe[3 + 6 * f + d] = sc[2 * f]; pe[3 + 6 * f + 3 + d] = sc[2 * f + 1]; }
             }
 #pragma unroll
             for (int k = 39; k < 48; ++k) pe[k] = 0.f;
 #pragma unroll
             for (int c8 = 0; c8 < 6; ++c8) st_a8(t, 4 + c8, &pe[c8 * 8]);      // columns 32..79
+            if (H0 && valid) {
+#pragma unroll
+                for (int k = 0; k < 39; ++k) H0[(size_t)k * Ps + p] = pe[k];
+            }
         }
 #pragma unroll
         for (int l = 0; l < 32 / C; ++l) {
@@ -224,6 +223,10 @@ sdf_forward_tc_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
                     for (int d = 0; d < 3; ++d)
 #pragma unroll
                         for (int c = 0; c < C; ++c) DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p] = dfeat[d][c];
+                    if (H0) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) H0[(size_t)(39 + l * C + c) * Ps + p] = feat[c];
+                    }
                 }
             } else {
 #pragma unroll
@@ -384,7 +387,7 @@ sdf_forward_tc_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
 }
 
 int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
-                          float *grad, float *Z, float *R, float *DYDX, cudaStream_t st) {
+                          float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t pairs = div_up(div_up(P, 128), 2);
     const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
@@ -396,7 +399,7 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
                    "nicer_sdf_forward(tc A)");                                                                          \
         NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tc_b_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), \
                    "nicer_sdf_forward(tc B)");                                                                          \
-        sdf_forward_tc_a_kernel<CC><<<grid, TCF_THREADS, smem_a, st>>>(*net, ls, pa, x, P, flags, sdf, feat_fm, Z, DYDX);   \
+        sdf_forward_tc_a_kernel<CC><<<grid, TCF_THREADS, smem_a, st>>>(*net, ls, pa, x, P, flags, sdf, feat_fm, Z, DYDX, H0); \
         sdf_forward_tc_b_kernel<CC><<<grid, TCF_THREADS, smem_b, st>>>(*net, ls, pb, x, P, flags, grad, Z, R, DYDX);        \
     } while (0)
     switch (net->grid.C) {
@@ -414,12 +417,12 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
 // Kernel T: tangent pass (forward-mode derivative of the network in direction g_bar = dL/d(d sdf/dx)):
 //   t_0 = J g_bar, u_1 = W_0 t_0, tan_l = u_l * sp'(z_l), u_{l+1} = W_l tan_l
 // and the per-layer buffers the weight-gradient GEMMs and kernel R need: TAN, QB = r_l sp'(z_l), AB = a_l,
-// ZB <- u_l r_l sp''(z_l) (the second-order part of dL/dz_l), T0 (all rows) and the PE rows of H0.
+// ZB <- u_l r_l sp''(z_l) (the second-order part of dL/dz_l) and T0.
 template <int C>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 sdf_backward_tc_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
                          uint32_t P, const float *Z, const float *R, const float *DYDX, const float *g_grad, float *ZB,
-                         float *QB, float *AB, float *TAN, float *H0, float *T0) {
+                         float *QB, float *AB, float *TAN, float *T0) {
     extern __shared__ __align__(16) float smem[];
     __shared__ TcfShared sh;
     LevelInfo *lv;
@@ -444,24 +447,21 @@ sdf_backward_tc_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 tp[d] = gg[d];
-                if (valid) { T0[(size_t)d * Ps + p] = gg[d]; H0[(size_t)d * Ps + p] = x[d]; }
+                if (valid) T0[(size_t)d * Ps + p] = gg[d];
             }
-            float fr = 1.0f;
 #pragma unroll
-            for (int f = 0; f < 6; ++f) {
+            for (int d = 0; d < 3; ++d) {
+                float sc[12];
+                pe_sincos<6, true>(x[d], sc);
+                float fr = 1.0f;
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    float s, c;
-                    sincosf(x[d] * fr, &s, &c);
+                for (int f = 0; f < 6; ++f) {
                     const int ks = 3 + 6 * f + d, kc = ks + 3;
-                    const float ts = fr * c * gg[d], tcv = -fr * s * gg[d];
+                    const float ts = fr * sc[2 * f + 1] * gg[d], tcv = -fr * sc[2 * f] * gg[d];
                     tp[ks] = ts; tp[kc] = tcv;
-                    if (valid) {
-                        T0[(size_t)ks * Ps + p] = ts; H0[(size_t)ks * Ps + p] = s;
-                        T0[(size_t)kc * Ps + p] = tcv; H0[(size_t)kc * Ps + p] = c;
-                    }
+                    if (valid) { T0[(size_t)ks * Ps + p] = ts; T0[(size_t)kc * Ps + p] = tcv; }
+                    fr *= 2.0f;
                 }
-                fr *= 2.0f;
             }
 #pragma unroll
             for (int k = 39; k < 48; ++k) tp[k] = 0.f;
@@ -524,12 +524,12 @@ sdf_backward_tc_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
 
 // Kernel R: reverse pass.  abar_n = W_n^T [g_sdf, g_feat],  zbar_l = abar_l sp'(z_l) + ZB_l (second-order part from
 // kernel T),  abar_{l-1} = W_{l-1}^T zbar_l,  hbar_0 = W_0^T zbar_1,  r_0 = W_0^T q_1 (for the second-order terms);
-// writes zbar_l into ZB, the grid rows of H0, scatters first- and second-order grid gradients, accumulates dL/dx.
+// writes zbar_l into ZB, scatters first- and second-order grid gradients, accumulates dL/dx.
 template <int C>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
                          uint32_t P, const float *Z, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
-                         const float *g_grad, float *grad_x, float *grad_table, float *ZB, const float *QB, float *H0) {
+                         const float *g_grad, float *grad_x, float *grad_table, float *ZB, const float *QB) {
     extern __shared__ __align__(16) float smem[];
     __shared__ TcfShared sh;
     LevelInfo *lv;
@@ -591,6 +591,7 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
         // ---- hbar_0: PE part -> dL/dx, grid part kept for the scatter
         float xb[3];
         float gy1[32];
+        float pesc[36];     // sin/cos of the PE, reused for the second-order term below
         {
             float hp[40];
 #pragma unroll
@@ -599,16 +600,15 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
             for (int c8 = 0; c8 < 4; ++c8) ld_d8(t, c8, &gy1[c8 * 8]);
             tc::wait_ld();
             xb[0] = hp[0]; xb[1] = hp[1]; xb[2] = hp[2];
-            float fr = 1.0f;
 #pragma unroll
-            for (int f = 0; f < 6; ++f) {
+            for (int d = 0; d < 3; ++d) {
+                pe_sincos<6, true>(x[d], &pesc[12 * d]);
+                float fr = 1.0f;
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    float s, c;
-                    sincosf(x[d] * fr, &s, &c);
-                    xb[d] += fr * (c * hp[3 + 6 * f + d] - s * hp[3 + 6 * f + 3 + d]);
+                for (int f = 0; f < 6; ++f) {
+                    xb[d] += fr * (pesc[12 * d + 2 * f + 1] * hp[3 + 6 * f + d] - pesc[12 * d + 2 * f] * hp[3 + 6 * f + 3 + d]);
+                    fr *= 2.0f;
                 }
-                fr *= 2.0f;
             }
         }
         // ---- r_0 = W_0^T q_1 (second-order terms)
@@ -620,16 +620,14 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
 #pragma unroll
             for (int c8 = 0; c8 < 5; ++c8) ld_d8(t, 4 + c8, &rp[c8 * 8]);
             tc::wait_ld();
-            float fr = 1.0f;
 #pragma unroll
-            for (int f = 0; f < 6; ++f) {
+            for (int d = 0; d < 3; ++d) {
+                float fr = 1.0f;
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    float s, c;
-                    sincosf(x[d] * fr, &s, &c);
-                    xb[d] += gg[d] * (fr * fr) * (-s * rp[3 + 6 * f + d] - c * rp[3 + 6 * f + 3 + d]);
+                for (int f = 0; f < 6; ++f) {
+                    xb[d] += gg[d] * (fr * fr) * (-pesc[12 * d + 2 * f] * rp[3 + 6 * f + d] - pesc[12 * d + 2 * f + 1] * rp[3 + 6 * f + 3 + d]);
+                    fr *= 2.0f;
                 }
-                fr *= 2.0f;
             }
         }
         float xu[3] = {0.f, 0.f, 0.f};
@@ -645,9 +643,6 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
                     for (int d = 0; d < 3; ++d) xu[d] += gy1[l * C + c] * dyv[(l * 3 + d) * C + c];
                 const LevelInfo li = lv[l];
                 Cell3 cell = locate3(li, u);
-                float feat[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) feat[c] = 0.f;
                 if (cell.inside && valid) {
                     uint32_t idx[8];
                     corner_indices(li, cell, idx);
@@ -658,20 +653,12 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
                     corner_dweights(cell, 2, dw2);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        float val[C], v[C];
-                        load_entry<C>(net.grid.table, li, idx[k], val);
+                        float v[C];
                         const float w2 = dw0[k] * ggu[0] + dw1[k] * ggu[1] + dw2[k] * ggu[2];
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            feat[c] += wt[k] * val[c];
-                            v[c] = wt[k] * gy1[l * C + c] + w2 * gy2[c];
-                        }
+                        for (int c = 0; c < C; ++c) v[c] = wt[k] * gy1[l * C + c] + w2 * gy2[c];
                         scatter_entry<C>(grad_table, li, idx[k], v);
                     }
-                }
-                if (valid) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) H0[(size_t)(39 + l * C + c) * Ps + p] = feat[c];
                 }
             }
         }
@@ -685,7 +672,7 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
 
 int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
                            const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
-                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *H0, float *T0, cudaStream_t st) {
+                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t pairs = div_up(div_up(P, 128), 2);
     const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
@@ -697,9 +684,9 @@ int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t 
                    "nicer_sdf_backward(tc T)");                                                                          \
         NICER_CUDA(cudaFuncSetAttribute(sdf_backward_tc_r_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r), \
                    "nicer_sdf_backward(tc R)");                                                                          \
-        sdf_backward_tc_t_kernel<CC><<<grid, TCF_THREADS, smem_t, st>>>(*net, ls, pt, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, H0, T0); \
+        sdf_backward_tc_t_kernel<CC><<<grid, TCF_THREADS, smem_t, st>>>(*net, ls, pt, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0); \
         sdf_backward_tc_r_kernel<CC><<<grid, TCF_THREADS, smem_r, st>>>(*net, ls, pr, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, \
-                                                                        grad_table, ZB, QB, H0);                         \
+                                                                        grad_table, ZB, QB);                             \
     } while (0)
     switch (net->grid.C) {
         case 2: LAUNCH(2); break;

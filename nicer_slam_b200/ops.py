@@ -158,12 +158,13 @@ class SdfNetFn(torch.autograd.Function):
         Z = torch.empty(n * HIDDEN, P, device=dev)
         R = torch.empty((n - 1) * HIDDEN, P, device=dev) if n > 1 else None
         DYDX = torch.empty(meta.grid.L * 3 * meta.grid.C, P, device=dev)
+        H0 = torch.empty(meta.d_in, P, device=dev)      # network input, kept for the layer-0 weight gradient
         net = _sdf_struct(meta, table_d, offsets, wb)
         flags = 0 if want_feat else F_NO_FEAT
         check(lib().nicer_sdf_forward(C.byref(net), ptr(x), P, flags, ptr(sdf), ptr(feat_fm), ptr(grad), ptr(Z),
-                                      ptr(R), ptr(DYDX), stream()), "nicer_sdf_forward")
+                                      ptr(R), ptr(DYDX), ptr(H0), stream()), "nicer_sdf_forward")
         ctx.meta, ctx.want_feat = meta, want_feat
-        ctx.save_for_backward(x, table_d, offsets, Z, R, DYDX, *wb)
+        ctx.save_for_backward(x, table_d, offsets, Z, R, DYDX, H0, *wb)
         ctx.set_materialize_grads(False)
         nfeat = meta.d_out - 1
         feat = feat_fm[:nfeat].t() if want_feat else torch.zeros(P, 0, device=dev)
@@ -171,7 +172,7 @@ class SdfNetFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_sdf, g_feat, g_grad):
-        x, table, offsets, Z, R, DYDX, *wb = ctx.saved_tensors
+        x, table, offsets, Z, R, DYDX, H0, *wb = ctx.saved_tensors
         meta = ctx.meta
         n, P, dev = meta.n_hidden, x.shape[0], x.device
         nfeat = meta.d_out - 1
@@ -188,11 +189,10 @@ class SdfNetFn(torch.autograd.Function):
         grad_table = torch.zeros_like(table)
         ZB = torch.empty(n * HIDDEN, P, device=dev)
         QB, AB, TAN = torch.empty_like(ZB), torch.empty_like(ZB), torch.empty_like(ZB)
-        H0 = torch.empty(meta.d_in, P, device=dev)
         T0 = torch.empty(meta.d_in, P, device=dev)
         net = _sdf_struct(meta, table, offsets, wb)
         check(lib().nicer_sdf_backward(C.byref(net), ptr(x), P, ptr(Z), ptr(R), ptr(DYDX), ptr(gs), ptr(gf), ptr(gg),
-                                       ptr(grad_x), ptr(grad_table), ptr(ZB), ptr(QB), ptr(AB), ptr(TAN), ptr(H0),
+                                       ptr(grad_x), ptr(grad_table), ptr(ZB), ptr(QB), ptr(AB), ptr(TAN),
                                        ptr(T0), stream()), "nicer_sdf_backward")
         grads = []
         for l in range(n + 1):
@@ -226,7 +226,7 @@ def sdf_values(x, nets, out=None):
         net = _sdf_struct(meta, table.detach(), offsets, wb)
         flags = F_SDF_ONLY | (F_ACCUMULATE if i > 0 else 0)
         check(lib().nicer_sdf_forward(C.byref(net), ptr(x), P, flags, ptr(sdf), None, None, None, None, None,
-                                      stream()), "nicer_sdf_forward")
+                                      None, stream()), "nicer_sdf_forward")
     return sdf.view(P, 1)
 
 
@@ -246,16 +246,19 @@ class ColorNetFn(torch.autograd.Function):
         rgb = torch.empty(P, 3, device=dev)
         A_fm = torch.empty(n * HIDDEN, P, device=dev)
         DYDX = torch.empty(meta.grid.L * 3 * meta.grid.C, P, device=dev) if want_dx else None
+        # network input kept for the layer-0 weight gradient; the kernel writes every row but the feature block
+        # [33, 33+F), which is feat_fm itself
+        H0 = torch.empty(meta.d_in, P, device=dev)
         net = _color_struct(meta, table_d, offsets, wb)
         check(lib().nicer_color_forward(C.byref(net), ptr(x), ptr(view), ptr(normals), ptr(feat_fm), P, ptr(rgb),
-                                        ptr(A_fm), ptr(DYDX), stream()), "nicer_color_forward")
+                                        ptr(A_fm), ptr(DYDX), ptr(H0), stream()), "nicer_color_forward")
         ctx.meta, ctx.has_grid = meta, has_grid
-        ctx.save_for_backward(x, view, normals, feat_fm, table_d, offsets, rgb, A_fm, DYDX, *wb)
+        ctx.save_for_backward(x, view, normals, feat_fm, table_d, offsets, rgb, A_fm, DYDX, H0, *wb)
         return rgb
 
     @staticmethod
     def backward(ctx, g_rgb):
-        x, view, normals, feat_fm, table, offsets, rgb, A_fm, DYDX, *wb = ctx.saved_tensors
+        x, view, normals, feat_fm, table, offsets, rgb, A_fm, DYDX, H0, *wb = ctx.saved_tensors
         meta = ctx.meta
         P, dev, n = x.shape[0], x.device, meta.n_hidden
         g_rgb = _c(g_rgb)
@@ -267,19 +270,18 @@ class ColorNetFn(torch.autograd.Function):
         grad_table = torch.zeros_like(table) if scatter else None
         ZB = torch.empty(n * HIDDEN, P, device=dev)
         OB = torch.empty(3, P, device=dev)
-        H0 = torch.empty(meta.d_in, P, device=dev)
         net = _color_struct(meta, table, offsets, wb)
         check(lib().nicer_color_backward(C.byref(net), ptr(x), ptr(view), ptr(normals), ptr(feat_fm), P, ptr(rgb),
                                          ptr(A_fm), ptr(DYDX), ptr(g_rgb), ptr(grad_x), ptr(grad_view),
                                          ptr(grad_normals), ptr(grad_feat_fm), ptr(grad_table), ptr(ZB), ptr(OB),
-                                         ptr(H0), stream()), "nicer_color_backward")
+                                         stream()), "nicer_color_backward")
         grads = []
         for l in range(n + 1):
             W = wb[2 * l]
             dW, db = torch.zeros_like(W), torch.zeros(W.shape[0], device=dev)
             if l == 0:
                 # input = [x, PE(view), normals (33) | feat (F) | grid]: the feature block reads feat_fm in place, the
-                # kernels only materialise the 33 + L*C other rows of H0
+                # forward kernel only materialised the 33 + L*C other rows of H0
                 nf = meta.feature
                 outer_accum(ZB[:HIDDEN], H0[:33], dW, db)
                 outer_accum(ZB[:HIDDEN], feat_fm, dW, None, col0=33)

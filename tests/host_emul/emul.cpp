@@ -87,34 +87,34 @@ struct HostColor {
     }
 
 extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf,
-                                 float *feat_fm, float *grad, float *Z, float *R, float *DYDX, void *) {
+                                 float *feat_fm, float *grad, float *Z, float *R, float *DYDX, float *H0, void *) {
     HostSdf h(*net);
     float col[COL_ROWS];
     for (uint32_t p = 0; p < P; ++p)
-        DISPATCH_C(net->grid.C, (sdf_forward_sample<CC>(h.nv, x, p, P, flags, col, 1, sdf, feat_fm, grad, Z, R, DYDX)));
+        DISPATCH_C(net->grid.C, (sdf_forward_sample<CC>(h.nv, x, p, P, flags, col, 1, sdf, feat_fm, grad, Z, R, DYDX, H0)));
     return 0;
 }
 
 extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
                                   const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
                                   const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
-                                  float *AB, float *TAN, float *H0, float *T0, void *) {
+                                  float *AB, float *TAN, float *T0, void *) {
     HostSdf h(*net);
     float col[COL_ROWS];
     for (uint32_t p = 0; p < P; ++p)
         DISPATCH_C(net->grid.C, (sdf_backward_sample<CC>(h.nv, x, p, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x,
-                                                         grad_table, ZB, QB, AB, TAN, H0, T0, col, 1)));
+                                                         grad_table, ZB, QB, AB, TAN, T0, col, 1)));
     return 0;
 }
 
 extern "C" int nicer_color_forward(const nicer_color_net_t *net, const float *x, const float *view,
                                    const float *normals, const float *feat_fm, uint32_t P, float *rgb, float *A_fm,
-                                   float *DYDX, void *) {
+                                   float *DYDX, float *H0, void *) {
     HostColor h(*net);
     float col[NICER_W];
     const uint32_t C = net->grid.table ? net->grid.C : 2;
     for (uint32_t p = 0; p < P; ++p)
-        DISPATCH_C(C, (color_forward_sample<CC>(h.nv, x, view, normals, feat_fm, p, P, col, 1, rgb, A_fm, DYDX)));
+        DISPATCH_C(C, (color_forward_sample<CC>(h.nv, x, view, normals, feat_fm, p, P, col, 1, rgb, A_fm, DYDX, H0)));
     return 0;
 }
 
@@ -122,13 +122,13 @@ extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x
                                     const float *normals, const float *feat_fm, uint32_t P, const float *rgb,
                                     const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
                                     float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table,
-                                    float *ZB, float *OB, float *H0, void *) {
+                                    float *ZB, float *OB, void *) {
     HostColor h(*net);
     float col[NICER_W];
     const uint32_t C = net->grid.table ? net->grid.C : 2;
     for (uint32_t p = 0; p < P; ++p)
         DISPATCH_C(C, (color_backward_sample<CC>(h.nv, x, view, normals, feat_fm, p, P, rgb, A_fm, DYDX, g_rgb, grad_x,
-                                                grad_view, grad_normals, grad_feat_fm, grad_table, ZB, OB, H0, col, 1)));
+                                                grad_view, grad_normals, grad_feat_fm, grad_table, ZB, OB, col, 1)));
     return 0;
 }
 
