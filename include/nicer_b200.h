@@ -109,12 +109,18 @@ int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, ui
  *     ZB  [n_hidden*64][P]  dL/dz_l          QB  [n_hidden*64][P]  q_l = r_l * softplus'(z_l)
  *     AB  [n_hidden*64][P]  a_l              TAN [n_hidden*64][P]  tangent of a_l in direction g_grad
  *     T0  [d_in][P]         tangent of the network input (H0, the input itself, is saved by the forward)
+ *   Workspace: GY [2*L*C][P]  dL/d(enc) (first-order rows, then the second-order rows) handed from the MLP backward
+ *                             kernel to the grid-scatter kernel
  */
 int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P,
                        const float *Z, const float *R, const float *DYDX,
                        const float *g_sdf, const float *g_feat_fm, const float *g_grad,
                        float *grad_x, float *grad_table,
-                       float *ZB, float *QB, float *AB, float *TAN, float *T0, void *stream);
+                       float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, void *stream,
+                       void *scatter_stream);
+/* scatter_stream (both backward calls): stream the grid-scatter kernel runs on, after everything enqueued on `stream`
+ * by the call (NULL or == stream: same stream).  grad_table is complete when scatter_stream has drained; the caller
+ * joins the streams.  Lets the atomics-bound scatter overlap with the weight-gradient GEMMs that follow. */
 
 typedef struct {
     nicer_grid_t grid;         /* grid.table == NULL: no color grid (use_grid_feature=false) */
@@ -136,12 +142,13 @@ int nicer_color_forward(const nicer_color_net_t *net, const float *x, const floa
 
 /* g_rgb [P,3] upstream.  Outputs: grad_x (+=, NULL ok), grad_view [P,3] (written, NULL ok),
  * grad_normals [P,3] (written), grad_feat_fm [64][P] (written), grad_table (atomics, NULL when detached),
- * ZB [n_hidden*64][P] dL/dz_l, OB [3][P] dL/d(pre-sigmoid) (for nicer_outer_accum). */
+ * ZB [n_hidden*64][P] dL/dz_l, OB [3][P] dL/d(pre-sigmoid) (for nicer_outer_accum).
+ * Workspace: GY [L*C][P] dL/d(enc) for the grid-scatter kernel (NULL ok when there is no grid or it is detached). */
 int nicer_color_backward(const nicer_color_net_t *net, const float *x, const float *view,
                          const float *normals, const float *feat_fm, uint32_t P, const float *rgb,
                          const float *A_fm, const float *DYDX, const float *g_rgb,
                          float *grad_x, float *grad_view, float *grad_normals, float *grad_feat_fm,
-                         float *grad_table, float *ZB, float *OB, void *stream);
+                         float *grad_table, float *ZB, float *OB, float *GY, void *stream, void *scatter_stream);
 
 /* C[M,N] (row stride ldc) += A[M][P] * B[N][P]^T ;  bias[M] += rowsum(A) when bias != NULL.
  * A, B feature-major with row strides lda, ldb (>= P).  M <= 64, N <= 144. */

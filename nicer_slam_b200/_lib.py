@@ -39,9 +39,9 @@ _SIGS = {
     "nicer_hash_encode_second_backward": [_fp, _fp, _fp, _fp, _u32, _u32, _u32, _u32, C.c_float, _u32, C.c_int, _fp,
                                           _fp, _fp, _fp, _fp],
     "nicer_sdf_forward": [C.POINTER(SdfNetT), _fp, _u32, _u32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
-    "nicer_sdf_backward": [C.POINTER(SdfNetT), _fp, _u32] + [_fp] * 14,
+    "nicer_sdf_backward": [C.POINTER(SdfNetT), _fp, _u32] + [_fp] * 16,
     "nicer_color_forward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32, _fp, _fp, _fp, _fp, _fp],
-    "nicer_color_backward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32] + [_fp] * 12,
+    "nicer_color_backward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32] + [_fp] * 14,
     "nicer_outer_accum": [_fp, _u32, _u32, _fp, _u32, _u32, _u32, _fp, _u32, _fp, _fp],
     "nicer_composite_forward": [_fp] * 6 + [_u32, _u32, _u32] + [_fp] * 6,
     "nicer_composite_backward": [_fp] * 6 + [_u32, _u32, _u32] + [_fp] * 11,
@@ -52,7 +52,7 @@ _SIGS = {
 
 _handle = None
 launch_count = 0          # kernels launched through this binding (bench.py's gpu_launches)
-_LAUNCHES = {"nicer_hash_encode_backward": 2}
+_LAUNCHES = {"nicer_hash_encode_backward": 2, "nicer_sdf_forward": 2, "nicer_sdf_backward": 3, "nicer_color_backward": 2}
 
 
 def _bind(h):

@@ -126,7 +126,7 @@ int launch_color_forward_tc(const nicer_color_net_t *net, const float *x, const 
 int launch_color_backward_tc(const nicer_color_net_t *net, const float *x, const float *view, const float *normals, uint32_t P,
                              const float *rgb, const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
                              float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table, float *ZB, float *OB,
-                             cudaStream_t st);
+                             float *GY, cudaStream_t st, cudaStream_t scatter_st);
 
 }  // namespace nicer
 
@@ -169,16 +169,17 @@ extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x
                                     const float *normals, const float *feat_fm, uint32_t P, const float *rgb,
                                     const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
                                     float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table,
-                                    float *ZB, float *OB, void *stream) {
+                                    float *ZB, float *OB, float *GY, void *stream, void *scatter_stream) {
     if (int e = check_color_net(net, "nicer_color_backward")) return e;
     if (P == 0) return 0;
     if (!x || !view || !normals || !feat_fm || !rgb || !A_fm || !g_rgb || !grad_normals || !grad_feat_fm || !ZB || !OB)
         NICER_FAIL(-1, "nicer_color_backward: NULL pointer");
-    if (net->grid.table && !net->grid_detached && !grad_table)
-        NICER_FAIL(-1, "nicer_color_backward: grad_table required when the grid is not detached");
+    if (net->grid.table && !net->grid_detached && (!grad_table || !GY))
+        NICER_FAIL(-1, "nicer_color_backward: grad_table and GY required when the grid is not detached");
     {
         const int r = launch_color_backward_tc(net, x, view, normals, P, rgb, A_fm, DYDX, g_rgb, grad_x, grad_view, grad_normals,
-                                               grad_feat_fm, grad_table, ZB, OB, (cudaStream_t)stream);
+                                               grad_feat_fm, grad_table, ZB, OB, GY, (cudaStream_t)stream,
+                                               (cudaStream_t)scatter_stream);
         if (r != 0) return r < 0 ? r : 0;
     }
     ColorSmemLayout lay = color_layout((int)net->n_hidden);

@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1)
 color_backward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, const ColorPlan pl, const float *__restrict__ X,
                          const float *__restrict__ V, const float *__restrict__ Nrm, uint32_t P, const float *__restrict__ rgb,
                          const float *__restrict__ A_fm, const float *__restrict__ DYDX, const float *__restrict__ g_rgb,
-                         float *grad_x, float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table, float *ZB,
-                         float *OB) {
+                         float *grad_x, float *grad_view, float *grad_normals, float *grad_feat_fm, float *ZB,
+                         float *OB, float *GY) {
     extern __shared__ __align__(16) float smem[];
     __shared__ TcfShared sh;
     const int tid = threadIdx.x;
@@ -316,32 +316,17 @@ color_backward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, cons
             }
         }
         ct_issue(t, pl, 2, NICER_W, NICER_W, smem);        // hbar block b (features) = W0b^T zbar_1; A still holds zbar_1
-        // grid: scatter + dL/dx through the grid while the MMAs run (indices and weights only, no table reads)
+        // grid: dL/dx through the grid; dL/d(enc) goes to the scatter kernel (grid_scatter.cu)
         float xu[3] = {0.f, 0.f, 0.f};
         if (has_grid && !detached) {
-            float u[3];
-            to_unit(x, df, u);
 #pragma unroll
             for (int l = 0; l < 32 / C; ++l) {
                 if (l < L) {
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
+                    for (int c = 0; c < C; ++c) {
 #pragma unroll
                         for (int d = 0; d < 3; ++d) xu[d] += gy[l * C + c] * dyv[(l * 3 + d) * C + c];
-                    const LevelInfo li = lv[l];
-                    Cell3 cell = locate3(li, u);
-                    if (cell.inside && valid) {
-                        uint32_t idx[8];
-                        corner_indices(li, cell, idx);
-                        float wt[8];
-                        corner_weights(cell, wt);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            float vv[C];
-#pragma unroll
-                            for (int c = 0; c < C; ++c) vv[c] = wt[k] * gy[l * C + c];
-                            scatter_entry<C>(grad_table, li, idx[k], vv);
-                        }
+                        if (valid) GY[(size_t)(l * C + c) * Ps + p] = gy[l * C + c];
                     }
                 }
             }
@@ -393,10 +378,13 @@ int launch_color_forward_tc(const nicer_color_net_t *net, const float *x, const 
     return 1;
 }
 
+int launch_grid_scatter(const nicer_grid_t *g, const float *x, uint32_t P, const float *GY1, const float *GY2,
+                        const float *g_grad, float *grad_table, cudaStream_t st);
+
 int launch_color_backward_tc(const nicer_color_net_t *net, const float *x, const float *view, const float *normals, uint32_t P,
                              const float *rgb, const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
                              float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table, float *ZB, float *OB,
-                             cudaStream_t st) {
+                             float *GY, cudaStream_t st, cudaStream_t scatter_st) {
     if (!tc_enabled() || net->n_hidden != 2 || net->multires_view != 4 || net->feature != 64) return 0;
     const bool has_grid = net->grid.table != nullptr;
     const LevelScales ls = host_level_scales(has_grid ? net->grid.L : 0, net->grid.S, net->grid.H);
@@ -409,7 +397,7 @@ int launch_color_backward_tc(const nicer_color_net_t *net, const float *x, const
         NICER_CUDA(cudaFuncSetAttribute(color_backward_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
                    "nicer_color_backward(tc)");                                                                            \
         color_backward_tc_kernel<CC><<<grid, TCF_THREADS, smem, st>>>(*net, ls, pl, x, view, normals, P, rgb, A_fm, DYDX, g_rgb, \
-                                                                      grad_x, grad_view, grad_normals, grad_feat_fm, grad_table, ZB, OB); \
+                                                                      grad_x, grad_view, grad_normals, grad_feat_fm, ZB, OB, GY); \
     } while (0)
     switch (has_grid ? net->grid.C : 2) {
         case 2: LAUNCH(2); break;
@@ -418,6 +406,14 @@ int launch_color_backward_tc(const nicer_color_net_t *net, const float *x, const
     }
 #undef LAUNCH
     NICER_CHECK_LAUNCH("nicer_color_backward(tc)");
+    if (has_grid && !net->grid_detached) {
+        if (scatter_st && scatter_st != st) {
+            if (int e = stream_fork(st, scatter_st)) return e;
+        } else {
+            scatter_st = st;
+        }
+        if (int e = launch_grid_scatter(&net->grid, x, P, GY, nullptr, nullptr, grad_table, scatter_st)) return e;
+    }
     return 1;
 }
 

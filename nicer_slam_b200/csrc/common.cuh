@@ -11,6 +11,7 @@ namespace nicer {
 
 void set_error(const char *fmt, ...);
 int num_sms();
+int stream_fork(cudaStream_t main_stream, cudaStream_t side);
 
 #define NICER_FAIL(code, ...)          \
     do {                               \

@@ -142,7 +142,8 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
 
 int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
                            const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
-                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st);
+                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, cudaStream_t st,
+                           cudaStream_t scatter_st);
 
 template <typename K>
 static int prep_kernel(K kernel, size_t smem_bytes, const char *who) {
@@ -195,16 +196,17 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
 extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
                                   const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
                                   const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
-                                  float *AB, float *TAN, float *T0, void *stream) {
+                                  float *AB, float *TAN, float *T0, float *GY, void *stream, void *scatter_stream) {
     if (int e = check_sdf_net(net, "nicer_sdf_backward")) return e;
     if (P == 0) return 0;
     if (!x || !Z || !DYDX || !grad_table || !ZB || !QB || !AB || !TAN || !T0)
         NICER_FAIL(-1, "nicer_sdf_backward: a required pointer is NULL");
     if (net->n_hidden > 1 && !R) NICER_FAIL(-1, "nicer_sdf_backward: R required for n_hidden > 1");
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_backward: n_hidden > 3 not built");
+    if (tc_enabled() && net->multires == 6 && !GY) NICER_FAIL(-1, "nicer_sdf_backward: GY workspace is NULL");
     if (tc_enabled() && net->multires == 6)
         return launch_sdf_backward_tc(net, x, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB, TAN, T0,
-                                      (cudaStream_t)stream);
+                                      GY, (cudaStream_t)stream, (cudaStream_t)scatter_stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);

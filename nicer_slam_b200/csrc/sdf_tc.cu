@@ -185,6 +185,173 @@ sdf_only_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcSmem
     if (warp == 0) tc::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Four tiles per SM.  The kernel above is TMEM-bound at two 128-point tiles per SM (A hi 72 + A lo 72 + D 64 columns
+// -> 256 of the 512 columns each), i.e. 8 warps per SM, and spends most of its time waiting on instruction latency.
+// This variant feeds the A operand in K-chunks of 32 columns (hi 32 + lo 32 + D 64 = 128 columns per tile): a layer
+// is 2 (hidden, K = 64) or 3 (layer 0, K = 72 = 32 + 32 + 8) accumulating MMA groups, each waited for before the
+// operand columns are overwritten.  A CTA holds two tiles (256 threads, one staged copy of the weights), two CTAs
+// fit an SM: 16 warps per SM.  Layer 0's first chunk (x and most of the PE) is issued before the grid gathers start.
+constexpr int T4_THREADS = 256;
+constexpr int T4_ALO = 32, T4_D = 64, T4_TILE_COLS = 128, T4_CTA_COLS = 256;
+
+struct Tile4 {
+    uint32_t tmem, lane_base;
+    uint64_t *bar;
+    uint32_t parity;
+    int id;
+    bool leader;
+};
+
+// MMAs for K-steps [ks0, ks0 + nks) of a staged [K/4][64][4] operand against the chunk columns [0, 8*nks) of the tile
+__device__ __forceinline__ void chunk_issue(Tile4 &t, uint32_t whi, uint32_t wlo, int ks0, int nks, bool acc) {
+    tc::wait_st();
+    tc::fence_before_sync();
+    asm volatile("bar.sync %0, 128;" ::"r"(t.id) : "memory");
+    if (t.leader) {
+        tc::fence_after_sync();
+        constexpr uint32_t IDESC = tc::idesc_tf32(128, NICER_W);
+        for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t bhi = tc::smem_desc(whi + (uint32_t)(ks0 + ks) * 2u * 1024u, 1024u, 128u);
+            const uint64_t blo = tc::smem_desc(wlo + (uint32_t)(ks0 + ks) * 2u * 1024u, 1024u, 128u);
+            const uint32_t ahi = t.tmem + ks * 8, alo = t.tmem + T4_ALO + ks * 8;
+            tc::mma_tf32_ts(t.tmem + T4_D, ahi, bhi, IDESC, (acc || ks > 0) ? 1u : 0u);
+            tc::mma_tf32_ts(t.tmem + T4_D, alo, bhi, IDESC, 1u);
+            tc::mma_tf32_ts(t.tmem + T4_D, ahi, blo, IDESC, 1u);
+        }
+        tc::mma_commit(t.bar);
+    }
+}
+__device__ __forceinline__ void chunk_wait(Tile4 &t) {
+    tc::mbar_wait(t.bar, t.parity);
+    t.parity ^= 1u;
+    __syncwarp();
+    tc::fence_after_sync();
+}
+// 8*N8 values -> chunk columns [0, 8*N8) (hi) and [32, 32 + 8*N8) (lo)
+template <int N8>
+__device__ __forceinline__ void chunk_store(const Tile4 &t, const float *v) {
+#pragma unroll
+    for (int c8 = 0; c8 < N8; ++c8) tc::tmem_st8_split(t.lane_base + c8 * 8, t.lane_base + T4_ALO + c8 * 8, v + c8 * 8);
+}
+
+template <int C>
+__global__ void __launch_bounds__(T4_THREADS, 2)
+sdf_only_tc4_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcSmemLayout lay, const float *__restrict__ X,
+                    uint32_t P, uint32_t accumulate, float *__restrict__ sdf) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, tile = tid >> 7;
+    const int n = (int)net.n_hidden;
+    const int L = (int)net.grid.L;
+    const int d_in = 39 + L * C;
+
+    for (int l = 0; l < n; ++l) {
+        tc_stage_weight(net.W[l], l == 0 ? d_in : NICER_W, l == 0 ? TC_K0 : NICER_W, smem + lay.w_hi[l], smem + lay.w_lo[l]);
+        for (int i = tid; i < NICER_W; i += T4_THREADS) smem[lay.bias[l] + i] = net.b[l][i];
+    }
+    for (int i = tid; i < NICER_W; i += T4_THREADS) smem[lay.wl_sdf + i] = net.W[n][i];
+    LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
+    for (int l = tid; l < L; l += T4_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_slot, T4_CTA_COLS);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    Tile4 t;
+    t.tmem = tmem_base_slot + (uint32_t)tile * T4_TILE_COLS;
+    t.lane_base = t.tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    t.bar = &bars[tile];
+    t.parity = 0;
+    t.id = 1 + tile;
+    t.leader = (tid & 127) == 0;
+    const float bl_sdf = net.b[n][0];
+    const float df = net.grid.divide_factor;
+    const float *wl = smem + lay.wl_sdf;
+
+    const uint32_t tiles = (P + 127u) / 128u;
+    for (uint32_t tt = blockIdx.x * 2 + tile; tt < tiles; tt += gridDim.x * 2) {
+        uint32_t p = tt * 128u + (tid & 127);
+        const bool valid = p < P;
+        if (!valid) p = P - 1;   // keep every warp converged for the .sync.aligned TMEM ops
+        // ---------------- layer 0, input in the natural order [x 3 | PE 36 | grid 32 | pad 1], chunks 32 + 32 + 8
+        {
+            const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+            float h0[TC_K0];
+            h0[0] = x[0]; h0[1] = x[1]; h0[2] = x[2];
+            // sin/cos(2^f x): one precise sincos per coordinate, then angle doubling (error grows ~2x per octave,
+            // <~ 2e-6 at 2^5: fine for the no-grad sampler pass, whose output only places samples)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                float s, c;
+                sincosf(x[d], &s, &c);
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    h0[3 + 6 * f + d] = s;
+                    h0[3 + 6 * f + 3 + d] = c;
+                    const float s2 = 2.0f * s * c, c2 = fmaf(-2.0f * s, s, 1.0f);
+                    s = s2; c = c2;
+                }
+            }
+            const uint32_t w0h = tc::smem_u32(smem + lay.w_hi[0]), w0l = tc::smem_u32(smem + lay.w_lo[0]);
+            chunk_store<4>(t, h0);
+            chunk_issue(t, w0h, w0l, 0, 4, false);           // runs while the grid levels are gathered
+            float u[3];
+            to_unit(x, df, u);
+            h0[71] = 0.f;
+#pragma unroll
+            for (int l = 0; l < 32 / C; ++l) {
+                float feat[C], dummy[3][C];
+                if (l < L) {
+                    encode_level<C, false>(net.grid.table, lv[l], u, feat, dummy);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) feat[c] = 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) h0[39 + l * C + c] = feat[c];
+            }
+            chunk_wait(t);
+            chunk_store<4>(t, h0 + 32);
+            chunk_issue(t, w0h, w0l, 4, 4, true);
+            chunk_wait(t);
+            chunk_store<1>(t, h0 + 64);
+            chunk_issue(t, w0h, w0l, 8, 1, true);
+            chunk_wait(t);
+        }
+        float a[NICER_W];
+        for (int l = 0; l < n; ++l) {
+#pragma unroll
+            for (int c8 = 0; c8 < NICER_W / 8; ++c8) tc::tmem_ld8(t.lane_base + T4_D + c8 * 8, &a[c8 * 8]);
+            tc::wait_ld();
+            const float *bias = smem + lay.bias[l];
+#pragma unroll
+            for (int j = 0; j < NICER_W; ++j) a[j] = softplus100_fast(a[j] + bias[j]);
+            if (l + 1 < n) {
+                const uint32_t wh = tc::smem_u32(smem + lay.w_hi[l + 1]), wlo_ = tc::smem_u32(smem + lay.w_lo[l + 1]);
+                chunk_store<4>(t, a);
+                chunk_issue(t, wh, wlo_, 0, 4, false);
+                chunk_wait(t);
+                chunk_store<4>(t, a + 32);
+                chunk_issue(t, wh, wlo_, 4, 4, true);
+                chunk_wait(t);
+            }
+        }
+        float s = bl_sdf;
+#pragma unroll
+        for (int k = 0; k < NICER_W; ++k) s += wl[k] * a[k];
+        if (valid) {
+            if (accumulate) sdf[p] += s; else sdf[p] = s;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_slot, T4_CTA_COLS);
+}
+
 static int g_tc_enabled = -1;
 bool tc_enabled() {
     if (g_tc_enabled < 0) {
@@ -202,6 +369,25 @@ int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, u
     const uint32_t tiles = div_up(P, TC_BLOCK);
     const uint32_t grid = tiles < (uint32_t)(2 * num_sms()) ? tiles : (uint32_t)(2 * num_sms());
     const uint32_t acc = (flags & NICER_SDF_ACCUMULATE) ? 1u : 0u;
+    static const int tiles_per_sm = [] { const char *e = getenv("NICER_TC_TILES"); return (e && e[0] == '2') ? 2 : 4; }();
+    if (tiles_per_sm == 4 && net->multires == 6) {
+        const uint32_t pairs = div_up(tiles, 2);
+        const uint32_t grid4 = pairs < (uint32_t)(2 * num_sms()) ? pairs : (uint32_t)(2 * num_sms());
+#define LAUNCH4(CC)                                                                                                  \
+    do {                                                                                                             \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_only_tc4_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
+                   "nicer_sdf_forward(tc4)");                                                                        \
+        sdf_only_tc4_kernel<CC><<<grid4, T4_THREADS, smem, st>>>(*net, ls, lay, x, P, acc, sdf);                     \
+    } while (0)
+        switch (net->grid.C) {
+            case 2: LAUNCH4(2); break;
+            case 4: LAUNCH4(4); break;
+            default: LAUNCH4(8); break;
+        }
+#undef LAUNCH4
+        NICER_CHECK_LAUNCH("nicer_sdf_forward(tc4)");
+        return 0;
+    }
 #define LAUNCH(CC)                                                                                                  \
     do {                                                                                                            \
         NICER_CUDA(cudaFuncSetAttribute(sdf_only_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \

@@ -529,7 +529,7 @@ template <int C>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
                          uint32_t P, const float *Z, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
-                         const float *g_grad, float *grad_x, float *grad_table, float *ZB, const float *QB) {
+                         const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY) {
     extern __shared__ __align__(16) float smem[];
     __shared__ TcfShared sh;
     LevelInfo *lv;
@@ -641,23 +641,12 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
                 for (int c = 0; c < C; ++c)
 #pragma unroll
                     for (int d = 0; d < 3; ++d) xu[d] += gy1[l * C + c] * dyv[(l * 3 + d) * C + c];
-                const LevelInfo li = lv[l];
-                Cell3 cell = locate3(li, u);
-                if (cell.inside && valid) {
-                    uint32_t idx[8];
-                    corner_indices(li, cell, idx);
-                    float wt[8], dw0[8], dw1[8], dw2[8];
-                    corner_weights(cell, wt);
-                    corner_dweights(cell, 0, dw0);
-                    corner_dweights(cell, 1, dw1);
-                    corner_dweights(cell, 2, dw2);
+                // grid gradients go to the scatter kernel (grid_scatter.cu): first-order rows, then second-order rows
+                if (valid) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        float v[C];
-                        const float w2 = dw0[k] * ggu[0] + dw1[k] * ggu[1] + dw2[k] * ggu[2];
-#pragma unroll
-                        for (int c = 0; c < C; ++c) v[c] = wt[k] * gy1[l * C + c] + w2 * gy2[c];
-                        scatter_entry<C>(grad_table, li, idx[k], v);
+                    for (int c = 0; c < C; ++c) {
+                        GY[(size_t)(l * C + c) * Ps + p] = gy1[l * C + c];
+                        GY[(size_t)((L + l) * C + c) * Ps + p] = gy2[c];
                     }
                 }
             }
@@ -670,9 +659,13 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
     tile_teardown(sh);
 }
 
+int launch_grid_scatter(const nicer_grid_t *g, const float *x, uint32_t P, const float *GY1, const float *GY2,
+                        const float *g_grad, float *grad_table, cudaStream_t st);
+
 int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
                            const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
-                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st) {
+                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, cudaStream_t st,
+                           cudaStream_t scatter_st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t pairs = div_up(div_up(P, 128), 2);
     const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
@@ -686,7 +679,7 @@ int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t 
                    "nicer_sdf_backward(tc R)");                                                                          \
         sdf_backward_tc_t_kernel<CC><<<grid, TCF_THREADS, smem_t, st>>>(*net, ls, pt, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0); \
         sdf_backward_tc_r_kernel<CC><<<grid, TCF_THREADS, smem_r, st>>>(*net, ls, pr, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, \
-                                                                        grad_table, ZB, QB);                             \
+                                                                        ZB, QB, GY);                                     \
     } while (0)
     switch (net->grid.C) {
         case 2: LAUNCH(2); break;
@@ -695,7 +688,13 @@ int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t 
     }
 #undef LAUNCH
     NICER_CHECK_LAUNCH("nicer_sdf_backward(tc)");
-    return 0;
+    if (scatter_st && scatter_st != st) {
+        if (int e = stream_fork(st, scatter_st)) return e;
+    } else {
+        scatter_st = st;
+    }
+    return launch_grid_scatter(&net->grid, x, P, GY, g_grad ? GY + (size_t)net->grid.L * net->grid.C * P : nullptr, g_grad,
+                               grad_table, scatter_st);
 }
 
 }  // namespace nicer

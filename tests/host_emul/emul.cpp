@@ -98,7 +98,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
 extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
                                   const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
                                   const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
-                                  float *AB, float *TAN, float *T0, void *) {
+                                  float *AB, float *TAN, float *T0, float * /*GY*/, void *, void *) {
     HostSdf h(*net);
     float col[COL_ROWS];
     for (uint32_t p = 0; p < P; ++p)
@@ -122,7 +122,7 @@ extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x
                                     const float *normals, const float *feat_fm, uint32_t P, const float *rgb,
                                     const float *A_fm, const float *DYDX, const float *g_rgb, float *grad_x,
                                     float *grad_view, float *grad_normals, float *grad_feat_fm, float *grad_table,
-                                    float *ZB, float *OB, void *) {
+                                    float *ZB, float *OB, float * /*GY*/, void *, void *) {
     HostColor h(*net);
     float col[NICER_W];
     const uint32_t C = net->grid.table ? net->grid.C : 2;
