@@ -108,11 +108,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float v[8]) {
 }
 
 // 3xTF32 split: hi keeps the top 19 bits (sign, exponent, 10 mantissa bits), lo = a - hi exactly
-// (round-to-nearest tf32: |lo| <= 2^-12 |a|, so the hardware's truncation of lo to tf32 costs <= 2^-23 |a|)
+// (round-to-nearest tf32: |lo| <= 2^-12 |a|, so the hardware's truncation of lo to tf32 costs <= 2^-23 |a|).
+// Rounding is done with two integer ALU ops (add half an ulp of tf32 to the magnitude, clear the 13 dropped bits =
+// round-to-nearest, ties away from zero, what cvt.rna.tf32.f32 does): cvt.rna runs on the XU pipe at ~4 results per
+// clock per SM (ncu: sm__inst_executed_pipe_xu at 75% in the weight-gradient kernel, which was bound by it).
 __device__ __forceinline__ float tf32_hi(float a) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
 }
 
 // write 8 values as (hi, lo) into the two A-operand column ranges
