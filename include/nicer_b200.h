@@ -181,6 +181,26 @@ int nicer_sampler_weights(const float *sdf, const float *x, const float *z, cons
 /* voxels[idx(x)] += 1 for every point with all |x_i| <= 0.99 (network.py:62-76). */
 int nicer_voxel_count(const float *x, uint32_t P, float *voxels, uint32_t voxel_res, void *stream);
 
+/* ---- camera / ray helpers (one kernel each; the reference runs them as ~200 elementwise kernels per iteration)
+ * nicer_pose_from_cam7            <- get_camera_from_tensor / quad2rotation   utils/general.py:52-100
+ *   cam7 [B,7] (quaternion w,x,y,z un-normalised, translation) -> pose [B,4,4] row-major c2w
+ * nicer_camera_rays               <- get_camera_params / lift                 utils/rend_util.py:68-93,107-129
+ *   uv [B,N,2], pose [B,4,4], K [B,4,4] -> dirs [B,N,3] (divided by the SQUARED norm, rend_util.py:92), cam_loc [B,3]
+ *   backward: g_dirs [B,N,3], g_loc [B,3] | NULL -> g_pose [B,4,4] (written; uv and K get no gradient)
+ * nicer_ray_points                <- points = cam_loc + z * dir, dirs repeated per sample   model/network.py:112-117
+ *   cam_loc [R,3], dirs [R,3], z [R,S] -> points [R*S,3], dirs_flat [R*S,3] | NULL
+ *   backward: g_points | NULL, g_dirs_flat | NULL ([R*S,3]) -> g_loc [R,3], g_dirs [R,3] (written; z gets no gradient) */
+int nicer_pose_from_cam7(const float *cam7, uint32_t B, float *pose, void *stream);
+int nicer_pose_from_cam7_backward(const float *cam7, const float *g_pose, uint32_t B, float *g_cam7, void *stream);
+int nicer_camera_rays(const float *uv, const float *pose, const float *K, uint32_t B, uint32_t N, float *dirs,
+                      float *cam_loc, void *stream);
+int nicer_camera_rays_backward(const float *uv, const float *pose, const float *K, uint32_t B, uint32_t N,
+                               const float *g_dirs, const float *g_loc, float *g_pose, void *stream);
+int nicer_ray_points(const float *cam_loc, const float *dirs, const float *z, uint32_t R, uint32_t S, float *points,
+                     float *dirs_flat, void *stream);
+int nicer_ray_points_backward(const float *z, uint32_t R, uint32_t S, const float *g_points, const float *g_dirs_flat,
+                              float *g_loc, float *g_dirs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,12 @@ _SIGS = {
     "nicer_sampler_weights": [_fp] * 4 + [_u32, _u32, _u32, _fp, _fp],
     "nicer_voxel_count": [_fp, _u32, _fp, _u32, _fp],
     "nicer_set_tensor_cores": [C.c_int],
+    "nicer_pose_from_cam7": [_fp, _u32, _fp, _fp],
+    "nicer_pose_from_cam7_backward": [_fp, _fp, _u32, _fp, _fp],
+    "nicer_camera_rays": [_fp, _fp, _fp, _u32, _u32, _fp, _fp, _fp],
+    "nicer_camera_rays_backward": [_fp, _fp, _fp, _u32, _u32, _fp, _fp, _fp, _fp],
+    "nicer_ray_points": [_fp, _fp, _fp, _u32, _u32, _fp, _fp, _fp],
+    "nicer_ray_points_backward": [_fp, _u32, _u32, _fp, _fp, _fp, _fp, _fp],
 }
 
 _handle = None

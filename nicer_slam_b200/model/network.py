@@ -102,11 +102,10 @@ class SLAMNetwork(nn.Module):
 
         z_vals, z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self, frame_idx, keyframe_list, mode)
         N_samples = z_vals.shape[1]
-        points = cam_loc.unsqueeze(1) + z_vals.unsqueeze(2) * ray_dirs.unsqueeze(1)
-        points_flat = points.reshape(-1, 3)
+        # points = cam_loc + z * dir and the per-sample view directions: one kernel (and one for the sums in backward)
+        points_flat, dirs_flat = ops.RayPointsFn.apply(cam_loc, ray_dirs, z_vals)
         if mode == "mapping":
             self.update_voxels(points_flat.detach())
-        dirs_flat = ray_dirs.unsqueeze(1).expand(-1, N_samples, -1).reshape(-1, 3)
 
         sdf, feature_vectors, gradients = self.implicit_network.get_outputs(points_flat, stage=stage)
         rgb_flat = self.rendering_network(points_flat, gradients, dirs_flat, feature_vectors, indices,

@@ -463,3 +463,80 @@ class _HashEncodeBackward(torch.autograd.Function):
 
 
 hash_encode = _HashEncode.apply
+
+
+# --------------------------------------------------------------------------------------------- camera / rays
+class PoseFromCam7Fn(torch.autograd.Function):
+    """cam7 [B,7] (quat wxyz un-normalised, translation) -> c2w [B,4,4]  (get_camera_from_tensor, general.py:52-100)."""
+
+    @staticmethod
+    def forward(ctx, cam7):
+        cam7 = _c(cam7.detach())
+        B = cam7.shape[0]
+        pose = torch.empty(B, 4, 4, device=cam7.device)
+        check(lib().nicer_pose_from_cam7(ptr(cam7), B, ptr(pose), stream()), "nicer_pose_from_cam7")
+        ctx.save_for_backward(cam7)
+        return pose
+
+    @staticmethod
+    def backward(ctx, g_pose):
+        (cam7,) = ctx.saved_tensors
+        g = torch.empty_like(cam7)
+        check(lib().nicer_pose_from_cam7_backward(ptr(cam7), ptr(_c(g_pose)), cam7.shape[0], ptr(g), stream()),
+              "nicer_pose_from_cam7_backward")
+        return g
+
+
+class CameraRaysFn(torch.autograd.Function):
+    """(uv [B,N,2], pose [B,4,4], K [B,4,4]) -> (ray_dirs [B,N,3], cam_loc [B,3])  (get_camera_params,
+    rend_util.py:68-93).  Differentiable w.r.t. the pose only, like the reference's use of it."""
+
+    @staticmethod
+    def forward(ctx, uv, pose, K):
+        uv, pose, K = _c(uv.detach()), _c(pose.detach()), _c(K.detach())
+        B, N = uv.shape[0], uv.shape[1]
+        dirs = torch.empty(B, N, 3, device=uv.device)
+        loc = torch.empty(B, 3, device=uv.device)
+        check(lib().nicer_camera_rays(ptr(uv), ptr(pose), ptr(K), B, N, ptr(dirs), ptr(loc), stream()), "nicer_camera_rays")
+        ctx.save_for_backward(uv, pose, K)
+        ctx.set_materialize_grads(False)
+        return dirs, loc
+
+    @staticmethod
+    def backward(ctx, g_dirs, g_loc):
+        uv, pose, K = ctx.saved_tensors
+        B, N = uv.shape[0], uv.shape[1]
+        if g_dirs is None:
+            g_dirs = torch.zeros(B, N, 3, device=uv.device)
+        g_pose = torch.empty(B, 4, 4, device=uv.device)
+        check(lib().nicer_camera_rays_backward(ptr(uv), ptr(pose), ptr(K), B, N, ptr(_c(g_dirs)),
+                                               ptr(_c(g_loc)) if g_loc is not None else None, ptr(g_pose), stream()),
+              "nicer_camera_rays_backward")
+        return None, g_pose, None
+
+
+class RayPointsFn(torch.autograd.Function):
+    """(cam_loc [R,3], ray_dirs [R,3], z [R,S]) -> (points [R*S,3], dirs_flat [R*S,3])  (network.py:112-117)."""
+
+    @staticmethod
+    def forward(ctx, cam_loc, ray_dirs, z):
+        cam_loc, ray_dirs, z = _c(cam_loc.detach()), _c(ray_dirs.detach()), _c(z.detach())
+        R, S = z.shape
+        points = torch.empty(R * S, 3, device=z.device)
+        dirs_flat = torch.empty(R * S, 3, device=z.device)
+        check(lib().nicer_ray_points(ptr(cam_loc), ptr(ray_dirs), ptr(z), R, S, ptr(points), ptr(dirs_flat), stream()),
+              "nicer_ray_points")
+        ctx.save_for_backward(z)
+        ctx.set_materialize_grads(False)
+        return points, dirs_flat
+
+    @staticmethod
+    def backward(ctx, g_points, g_dirs_flat):
+        (z,) = ctx.saved_tensors
+        R, S = z.shape
+        g_loc = torch.empty(R, 3, device=z.device)
+        g_dirs = torch.empty(R, 3, device=z.device)
+        check(lib().nicer_ray_points_backward(ptr(z), R, S, ptr(_c(g_points)) if g_points is not None else None,
+                                              ptr(_c(g_dirs_flat)) if g_dirs_flat is not None else None, ptr(g_loc),
+                                              ptr(g_dirs), stream()), "nicer_ray_points_backward")
+        return g_loc, g_dirs, None

@@ -29,10 +29,15 @@ def quad2rotation(quad):
 
 
 def get_camera_from_tensor(inputs):
-    """[7] or [B,7] (quat wxyz, translation) -> c2w [4,4] or [B,4,4]."""
+    """[7] or [B,7] (quat wxyz, translation) -> c2w [4,4] or [B,4,4].  fp32 inputs take the fused kernel
+    (ops.PoseFromCam7Fn, forward + hand-derived backward in one launch each); other dtypes the composite below."""
     single = inputs.dim() == 1
     if single:
         inputs = inputs.unsqueeze(0)
+    if inputs.dtype == torch.float32:
+        from .. import ops
+        RT = ops.PoseFromCam7Fn.apply(inputs)
+        return RT[0] if single else RT
     R = quad2rotation(inputs[:, :4])
     RT = torch.cat([R, inputs[:, 4:, None]], 2)
     bottom = torch.zeros(RT.shape[0], 1, 4, device=RT.device, dtype=RT.dtype)   # built on the device: no H2D copy,

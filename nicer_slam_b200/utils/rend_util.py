@@ -26,6 +26,9 @@ def get_camera_params(uv, pose, intrinsics):
     """uv [B,N,2], pose [B,4,4] (or [B,7] quat+t), K [B,4,4] -> ray_dirs [B,N,3], cam_loc [B,3].
     NB the directions are divided by their *squared* norm (rend_util.py:92); SLAMNetwork compensates with
     depth_scale (network.py:99-102)."""
+    if pose.dim() == 3 and pose.dtype == torch.float32 and uv.dtype == torch.float32:
+        from .. import ops       # one kernel forward, one backward (d/dpose); uv and K are not differentiated
+        return ops.CameraRaysFn.apply(uv, pose, intrinsics.to(uv.device))
     if pose.shape[1] == 7:
         cam_loc = pose[:, 4:]
         p = torch.eye(4, device=pose.device, dtype=pose.dtype).repeat(pose.shape[0], 1, 1)

@@ -10,6 +10,7 @@
 
 #include "../../include/nicer_b200.h"
 #include "../../nicer_slam_b200/csrc/color_sample.cuh"
+#include "../../nicer_slam_b200/csrc/geometry_math.cuh"
 #include "../../nicer_slam_b200/csrc/composite_math.cuh"
 
 using namespace nicer;
@@ -303,5 +304,78 @@ extern "C" int nicer_hash_encode_second_backward(const float *grad, const float 
         grad_grad[((size_t)l * B + b) * C + c] = r;
     }
     DISPATCH_C(C, (hash_bwd<CC>(grad, inputs, offsets, grad2_embeddings, B, L, S, H, ggx)));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- camera / ray helpers
+extern "C" int nicer_pose_from_cam7(const float *cam7, uint32_t B, float *pose, void *) {
+    for (uint32_t b = 0; b < B; ++b) pose_from_cam7(cam7 + 7 * (size_t)b, pose + 16 * (size_t)b);
+    return 0;
+}
+extern "C" int nicer_pose_from_cam7_backward(const float *cam7, const float *g_pose, uint32_t B, float *g_cam7, void *) {
+    for (uint32_t b = 0; b < B; ++b) pose_from_cam7_backward(cam7 + 7 * (size_t)b, g_pose + 16 * (size_t)b, g_cam7 + 7 * (size_t)b);
+    return 0;
+}
+extern "C" int nicer_camera_rays(const float *uv, const float *pose, const float *K, uint32_t B, uint32_t N, float *dirs,
+                                 float *cam_loc, void *) {
+    for (uint32_t b = 0; b < B; ++b) {
+        const float *P = pose + 16 * (size_t)b;
+        for (uint32_t n = 0; n < N; ++n) {
+            const size_t i = (size_t)b * N + n;
+            float v[3], p[3];
+            camera_ray(P, K + 16 * (size_t)b, uv[2 * i], uv[2 * i + 1], dirs + 3 * i, v, p);
+        }
+        cam_loc[3 * b] = P[3]; cam_loc[3 * b + 1] = P[7]; cam_loc[3 * b + 2] = P[11];
+    }
+    return 0;
+}
+extern "C" int nicer_camera_rays_backward(const float *uv, const float *pose, const float *K, uint32_t B, uint32_t N,
+                                          const float *g_dirs, const float *g_loc, float *g_pose, void *) {
+    for (uint32_t b = 0; b < B; ++b) {
+        const float *P = pose + 16 * (size_t)b;
+        double acc[9] = {0};
+        for (uint32_t n = 0; n < N; ++n) {
+            const size_t i = (size_t)b * N + n;
+            float d[3], v[3], p[3], gv[3];
+            camera_ray(P, K + 16 * (size_t)b, uv[2 * i], uv[2 * i + 1], d, v, p);
+            camera_ray_backward(v, g_dirs + 3 * i, gv);
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) acc[3 * r + c] += (double)gv[r] * p[c];
+        }
+        float *g = g_pose + 16 * (size_t)b;
+        for (int k = 0; k < 16; ++k) g[k] = 0.f;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) g[4 * r + c] = (float)acc[3 * r + c];
+            if (g_loc) g[4 * r + 3] = g_loc[3 * b + r];
+        }
+    }
+    return 0;
+}
+extern "C" int nicer_ray_points(const float *cam_loc, const float *dirs, const float *z, uint32_t R, uint32_t S, float *points,
+                                float *dirs_flat, void *) {
+    for (uint32_t r = 0; r < R; ++r)
+        for (uint32_t s = 0; s < S; ++s) {
+            const size_t i = (size_t)r * S + s;
+            for (int k = 0; k < 3; ++k) {
+                points[3 * i + k] = cam_loc[3 * (size_t)r + k] + fmul_exact(z[i], dirs[3 * (size_t)r + k]);
+                if (dirs_flat) dirs_flat[3 * i + k] = dirs[3 * (size_t)r + k];
+            }
+        }
+    return 0;
+}
+extern "C" int nicer_ray_points_backward(const float *z, uint32_t R, uint32_t S, const float *g_points, const float *g_dirs_flat,
+                                         float *g_loc, float *g_dirs, void *) {
+    for (uint32_t r = 0; r < R; ++r) {
+        double a[6] = {0};
+        for (uint32_t s = 0; s < S; ++s) {
+            const size_t i = (size_t)r * S + s;
+            for (int k = 0; k < 3; ++k) {
+                const float gp = g_points ? g_points[3 * i + k] : 0.f;
+                a[k] += gp;
+                a[3 + k] += (double)z[i] * gp + (g_dirs_flat ? g_dirs_flat[3 * i + k] : 0.f);
+            }
+        }
+        for (int k = 0; k < 3; ++k) { g_loc[3 * (size_t)r + k] = (float)a[k]; g_dirs[3 * (size_t)r + k] = (float)a[3 + k]; }
+    }
     return 0;
 }
