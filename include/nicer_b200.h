@@ -181,6 +181,30 @@ int nicer_sampler_weights(const float *sdf, const float *x, const float *z, cons
 /* voxels[idx(x)] += 1 for every point with all |x_i| <= 0.99 (network.py:62-76). */
 int nicer_voxel_count(const float *x, uint32_t P, float *voxels, uint32_t voxel_res, void *stream);
 
+/* ---- SLAMLoss terms over rays and eikonal points (model/loss.py:113-233, utils/MiDaS.py:6-140) in three kernels.
+ * A NULL prediction switches its term off.  terms[] receives the UNWEIGHTED term values and, in NICER_LOSS_SUM,
+ * sum_i w_i * term_i; every g_* output (NULL ok) receives d(that sum)/d(input).
+ * Workspace: acc double[8 + 5*B], maskf float[R] (the foreground & gt mask per ray). */
+#define NICER_LOSS_MAX_FRAMES 64
+enum { NICER_LOSS_RGB = 0, NICER_LOSS_DEPTH, NICER_LOSS_GT_DEPTH, NICER_LOSS_NORMAL_L1, NICER_LOSS_NORMAL_COS,
+       NICER_LOSS_EIKONAL, NICER_LOSS_SMOOTH, NICER_LOSS_SUM, NICER_LOSS_TERMS };
+typedef struct {
+    uint32_t R, S, B, N, G;             /* rays = B frames x N pixels, S samples per ray, G eikonal points */
+    uint32_t depth_mask_all;            /* depth term uses an all-ones mask (loss.py:171-173, Replica scan 4) */
+    const float *sdf;                   /* [R,S]: foreground = sign change along the ray (loss.py:165-167) */
+    const float *mask_gt;               /* [R]   : ground_truth["mask"] (> 0.5) */
+    const float *rgb_pred, *rgb_gt;     /* [R,3] : L1 */
+    const float *depth_pred;            /* [R]   : rendered depth (depth_values) */
+    const float *depth_gt;              /* [R]   : mono depth; target = depth_gt * 50 + 0.5 (loss.py:91); NULL: SSI term off */
+    const float *gt_depth;              /* [R]   : sensor-depth target, NULL: term off */
+    const float *gt_depth_valid;        /* [R]   : ground_truth["gt_depth"]; its > 0 entries are averaged */
+    const float *normal_pred, *normal_gt;          /* [R,3] */
+    const float *grad_theta, *grad_theta_nei;      /* [G,3] (nei NULL: no smoothness term) */
+    float w_rgb, w_depth, w_gt_depth, w_normal_l1, w_normal_cos, w_eik, w_smooth;
+    float *g_rgb, *g_depth, *g_normal, *g_theta, *g_theta_nei;
+} nicer_loss_t;
+int nicer_slam_loss(const nicer_loss_t *args, double *acc, float *maskf, float *terms, void *stream);
+
 /* ---- camera / ray helpers (one kernel each; the reference runs them as ~200 elementwise kernels per iteration)
  * nicer_pose_from_cam7            <- get_camera_from_tensor / quad2rotation   utils/general.py:52-100
  *   cam7 [B,7] (quaternion w,x,y,z un-normalised, translation) -> pose [B,4,4] row-major c2w

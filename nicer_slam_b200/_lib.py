@@ -22,6 +22,15 @@ class GridT(C.Structure):
                 ("divide_factor", C.c_float)]
 
 
+class LossT(C.Structure):
+    """nicer_loss_t (include/nicer_b200.h)."""
+    _fields_ = ([(n, C.c_uint32) for n in ("R", "S", "B", "N", "G", "depth_mask_all")]
+                + [(n, C.c_void_p) for n in ("sdf", "mask_gt", "rgb_pred", "rgb_gt", "depth_pred", "depth_gt", "gt_depth",
+                                             "gt_depth_valid", "normal_pred", "normal_gt", "grad_theta", "grad_theta_nei")]
+                + [(n, C.c_float) for n in ("w_rgb", "w_depth", "w_gt_depth", "w_normal_l1", "w_normal_cos", "w_eik", "w_smooth")]
+                + [(n, C.c_void_p) for n in ("g_rgb", "g_depth", "g_normal", "g_theta", "g_theta_nei")])
+
+
 class SdfNetT(C.Structure):
     _fields_ = [("grid", GridT), ("multires", _u32), ("n_hidden", _u32), ("d_out", _u32),
                 ("W", _fp * MAX_LAYERS), ("b", _fp * MAX_LAYERS)]
@@ -48,6 +57,7 @@ _SIGS = {
     "nicer_sampler_weights": [_fp] * 4 + [_u32, _u32, _u32, _fp, _fp],
     "nicer_voxel_count": [_fp, _u32, _fp, _u32, _fp],
     "nicer_set_tensor_cores": [C.c_int],
+    "nicer_slam_loss": [C.POINTER(LossT), _fp, _fp, _fp, _fp],
     "nicer_pose_from_cam7": [_fp, _u32, _fp, _fp],
     "nicer_pose_from_cam7_backward": [_fp, _fp, _u32, _fp, _fp],
     "nicer_camera_rays": [_fp, _fp, _fp, _u32, _u32, _fp, _fp, _fp],

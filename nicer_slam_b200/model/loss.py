@@ -77,6 +77,75 @@ class SLAMLoss(nn.Module):
         return _masked_mean(torch.abs(model_outputs["flow"] - tgt), m)
 
     def forward(self, model_outputs, ground_truth, keyframe_list=None, frame_idx=0, stage="coarse"):
+        if isinstance(self.rgb_loss, nn.L1Loss) and model_outputs["rgb_values"].dtype == torch.float32:
+            return self._forward_fused(model_outputs, ground_truth, keyframe_list, frame_idx, stage)
+        return self._forward_composite(model_outputs, ground_truth, keyframe_list, frame_idx, stage)
+
+    def _forward_fused(self, model_outputs, ground_truth, keyframe_list, frame_idx, stage):
+        """Same terms, with everything that is a reduction over rays / eikonal points in the fused kernels
+        (ops.SlamLossFn -> csrc/loss.cu); the warp and flow terms (masked L1 means over the warp / flow tensors) stay here."""
+        from .. import ops
+        rgb_pred, depth_pred = model_outputs["rgb_values"], model_outputs["depth_values"]
+        dev = rgb_pred.device
+        bs, N = depth_pred.shape[0], depth_pred.shape[1]
+
+        def flat(t, c):
+            return t.to(dev).reshape(-1, c) if c > 1 else t.to(dev).reshape(-1)
+
+        if self.assign_scale_shift_init:   # frame 0: supervise with the scaled mono depth (loss.py:179-184)
+            self.gt_depth_weight = 10 if frame_idx == 0 else 0
+        gt_depth_tgt = None
+        if self.gt_depth_weight > 0:
+            gt_depth_tgt = (ground_truth["depth"] * self.assign_scale if (self.assign_scale_shift_init and frame_idx == 0)
+                            else ground_truth["gt_depth"])
+        replica4 = (self.train_dataset is not None and "Replica" in getattr(self.train_dataset, "data_dir", "")
+                    and self.scan_id == 4)
+        use_normal = self.normal_l1_weight > 0 or self.normal_cos_weight > 0
+        use_eik = self.eikonal_weight > 0 and "grad_theta" in model_outputs
+        use_smooth = self.smooth_weight > 0.0
+        if use_smooth and "grad_theta" not in model_outputs:
+            raise KeyError("grad_theta")          # the reference's get_smooth_loss indexes it unconditionally
+        consts = dict(
+            sdf=model_outputs["sdf"], mask_gt=flat(ground_truth["mask"].float(), 1), rgb_gt=flat(ground_truth["rgb"], 3),
+            depth_gt=flat(ground_truth["depth"], 1) if self.depth_weight > 0 else None,
+            gt_depth=flat(gt_depth_tgt, 1) if gt_depth_tgt is not None else None,
+            gt_depth_valid=flat(ground_truth["gt_depth"], 1) if gt_depth_tgt is not None else None,
+            normal_gt=flat(ground_truth["normal"], 3) if use_normal else None,
+            B=bs, N=N, depth_mask_all=replica4,
+            w_rgb=self.rgb_loss_weight, w_depth=self.depth_weight, w_gt_depth=self.gt_depth_weight,
+            w_normal_l1=self.normal_l1_weight, w_normal_cos=self.normal_cos_weight,
+            w_eik=self.eikonal_weight if use_eik else 0.0, w_smooth=self.smooth_weight if use_smooth else 0.0)
+        theta = model_outputs["grad_theta"] if (use_eik or use_smooth) else None
+        nei = model_outputs["grad_theta_nei"] if use_smooth else None
+        fused, t = ops.SlamLossFn.apply(
+            rgb_pred.reshape(-1, 3), depth_pred.reshape(-1),
+            model_outputs["normal_map"].reshape(-1, 3) if use_normal else None, theta, nei, consts)
+
+        warp_loss = 0.0
+        if ("warp_output" in model_outputs) and self.warp_loss_weight > 0 and stage == "fine" and frame_idx != 0:
+            for patchsize, (gt_rgbs, sampled, mask, _ray_mask) in model_outputs["warp_output"].items():
+                if patchsize == 1 or self.warp_loss_type == "l1":
+                    warp_loss = warp_loss + _masked_mean(torch.abs(sampled - gt_rgbs), mask)
+                else:
+                    raise NotImplementedError("Strange patch loss type")
+        flow_loss = self.get_flow_loss(model_outputs, ground_truth, keyframe_list) if self.flow_weight > 0.0 else 0.0
+        loss = fused + self.flow_weight * flow_loss + self.warp_loss_weight * warp_loss
+        zero = 0.0
+        return {
+            "loss": loss,
+            "normal_l1": t[ops.LOSS_NORMAL_L1] if use_normal else zero,
+            "depth_loss": t[ops.LOSS_DEPTH] if self.depth_weight > 0 else zero,
+            "normal_cos": t[ops.LOSS_NORMAL_COS] if use_normal else zero,
+            "gt_depth_loss": t[ops.LOSS_GT_DEPTH] if gt_depth_tgt is not None else zero,
+            "flow_loss": self.flow_weight * flow_loss,
+            "rgb_loss": self.rgb_loss_weight * t[ops.LOSS_RGB],
+            "warp_loss": self.warp_loss_weight * warp_loss,
+            "smooth_loss": self.smooth_weight * (t[ops.LOSS_SMOOTH] if use_smooth else zero),
+            "eikonal_loss": self.eikonal_weight * (t[ops.LOSS_EIKONAL] if use_eik else zero),
+        }
+
+    def _forward_composite(self, model_outputs, ground_truth, keyframe_list=None, frame_idx=0, stage="coarse"):
+        """The reference's formulation op for op (used for rgb_loss classes other than L1 and non-fp32 outputs)."""
         rgb_pred, depth_pred = model_outputs["rgb_values"], model_outputs["depth_values"]
         dev = rgb_pred.device
         rgb_gt, depth_gt = ground_truth["rgb"].to(dev), ground_truth["depth"].to(dev)

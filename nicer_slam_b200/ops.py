@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ColorNetT, GridT, SdfNetT
+from ._lib import ColorNetT, GridT, LossT, SdfNetT
 
 
 def lib():
@@ -540,3 +540,63 @@ class RayPointsFn(torch.autograd.Function):
                                               ptr(_c(g_dirs_flat)) if g_dirs_flat is not None else None, ptr(g_loc),
                                               ptr(g_dirs), stream()), "nicer_ray_points_backward")
         return g_loc, g_dirs, None
+
+
+# --------------------------------------------------------------------------------------------- loss terms
+LOSS_RGB, LOSS_DEPTH, LOSS_GT_DEPTH, LOSS_NORMAL_L1, LOSS_NORMAL_COS, LOSS_EIKONAL, LOSS_SMOOTH, LOSS_SUM, LOSS_TERMS = range(9)
+
+
+class SlamLossFn(torch.autograd.Function):
+    """The ray / eikonal-point terms of SLAMLoss (loss.py:113-233) in three kernels.
+
+    forward(rgb_pred, depth_pred, normal_pred, grad_theta, grad_theta_nei, consts) -> (weighted sum of the terms,
+    terms [LOSS_TERMS] (unweighted, not differentiable)).  ``consts``: dict with sdf, mask_gt, rgb_gt, depth_gt, gt_depth,
+    gt_depth_valid, normal_gt (tensors or None), B, N, depth_mask_all and the weights w_*; a None prediction switches
+    its term off.  The gradients are computed in the forward kernels (they need nothing from upstream but a scale)."""
+
+    @staticmethod
+    def forward(ctx, rgb_pred, depth_pred, normal_pred, grad_theta, grad_theta_nei, k):
+        ref = next(t for t in (rgb_pred, depth_pred, normal_pred, grad_theta) if t is not None)
+        dev = ref.device
+
+        def cz(t):
+            return None if t is None else _c(t.detach().float())
+        sdf = cz(k["sdf"])
+        R, S = sdf.shape
+        a = LossT()
+        a.R, a.S, a.B, a.N = R, S, k["B"], k["N"]
+        a.G = 0 if grad_theta is None else grad_theta.shape[0]
+        a.depth_mask_all = int(bool(k.get("depth_mask_all", False)))
+        keep = {"sdf": sdf}
+        for name, t in (("mask_gt", k.get("mask_gt")), ("rgb_pred", rgb_pred), ("rgb_gt", k.get("rgb_gt")),
+                        ("depth_pred", depth_pred), ("depth_gt", k.get("depth_gt")), ("gt_depth", k.get("gt_depth")),
+                        ("gt_depth_valid", k.get("gt_depth_valid")), ("normal_pred", normal_pred),
+                        ("normal_gt", k.get("normal_gt")), ("grad_theta", grad_theta), ("grad_theta_nei", grad_theta_nei)):
+            keep[name] = cz(t)
+        for name, t in keep.items():
+            setattr(a, name, t.data_ptr() if t is not None else None)
+            if t is not None:
+                _lib.require(t, torch.float32, name)
+        for w in ("w_rgb", "w_depth", "w_gt_depth", "w_normal_l1", "w_normal_cos", "w_eik", "w_smooth"):
+            setattr(a, w, float(k.get(w, 0.0)))
+        grads = {}
+        for name, t, need in (("g_rgb", rgb_pred, 0), ("g_depth", depth_pred, 1), ("g_normal", normal_pred, 2),
+                              ("g_theta", grad_theta, 3), ("g_theta_nei", grad_theta_nei, 4)):
+            g = torch.empty(t.shape, device=dev) if (t is not None and ctx.needs_input_grad[need]) else None
+            grads[name] = g
+            setattr(a, name, g.data_ptr() if g is not None else None)
+        acc = torch.empty(8 + 5 * a.B, dtype=torch.float64, device=dev)
+        maskf = torch.empty(R, device=dev)
+        terms = torch.empty(LOSS_TERMS, device=dev)
+        check(lib().nicer_slam_loss(C.byref(a), C.c_void_p(acc.data_ptr()), ptr(maskf), ptr(terms), stream()), "nicer_slam_loss")
+        _lib.launch_count += 2
+        ctx.grads = grads
+        out_terms = terms.detach()
+        ctx.mark_non_differentiable(out_terms)
+        return terms[LOSS_SUM].clone(), out_terms
+
+    @staticmethod
+    def backward(ctx, g_sum, _g_terms):
+        g = ctx.grads
+        return tuple((g[n] * g_sum if g[n] is not None else None)
+                     for n in ("g_rgb", "g_depth", "g_normal", "g_theta", "g_theta_nei")) + (None,)

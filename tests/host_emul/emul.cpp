@@ -11,6 +11,7 @@
 #include "../../include/nicer_b200.h"
 #include "../../nicer_slam_b200/csrc/color_sample.cuh"
 #include "../../nicer_slam_b200/csrc/geometry_math.cuh"
+#include "../../nicer_slam_b200/csrc/loss_math.cuh"
 #include "../../nicer_slam_b200/csrc/composite_math.cuh"
 
 using namespace nicer;
@@ -377,5 +378,103 @@ extern "C" int nicer_ray_points_backward(const float *z, uint32_t R, uint32_t S,
         }
         for (int k = 0; k < 3; ++k) { g_loc[3 * (size_t)r + k] = (float)a[k]; g_dirs[3 * (size_t)r + k] = (float)a[3 + k]; }
     }
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------- SLAMLoss terms
+extern "C" int nicer_slam_loss(const nicer_loss_t *args, double *, float *maskf, float *terms, void *) {
+    const nicer_loss_t &a = *args;
+    double rgb = 0, nl1 = 0, ncos = 0, gtd = 0, gtd_cnt = 0, eik = 0, sm = 0;
+    std::vector<double> fr(5 * (size_t)a.B, 0.0);
+    for (uint32_t r = 0; r < a.R; ++r) {
+        bool pos = false, neg = false;
+        for (uint32_t s = 0; s < a.S; ++s) { const float v = a.sdf[(size_t)r * a.S + s]; pos |= v > 0.f; neg |= v < 0.f; }
+        const float m = (a.mask_gt && a.mask_gt[r] > 0.5f && pos && neg) ? 1.0f : 0.f;
+        maskf[r] = m;
+        if (a.rgb_pred)
+            for (int c = 0; c < 3; ++c) {
+                const float d = a.rgb_pred[3 * (size_t)r + c] - a.rgb_gt[3 * (size_t)r + c];
+                rgb += fabsf(d);
+                if (a.g_rgb) a.g_rgb[3 * (size_t)r + c] = a.w_rgb * sgnf(d) / (3.0f * (float)a.R);
+            }
+        if (a.normal_pred) {
+            float l1, cs, g[3];
+            normal_terms(a.normal_pred + 3 * (size_t)r, a.normal_gt + 3 * (size_t)r, m, a.w_normal_l1 / (float)a.R,
+                         a.w_normal_cos / (float)a.R, &l1, &cs, g);
+            nl1 += l1; ncos += cs;
+            if (a.g_normal) for (int c = 0; c < 3; ++c) a.g_normal[3 * (size_t)r + c] = g[c];
+        }
+        if (a.depth_pred && a.depth_gt) {
+            const float md = a.depth_mask_all ? 1.0f : m;
+            if (md != 0.f) {
+                const double p = a.depth_pred[r], t = a.depth_gt[r] * 50.0f + 0.5f;
+                double *f = fr.data() + 5 * (r / a.N);
+                f[0] += p * p; f[1] += p; f[2] += 1.0; f[3] += p * t; f[4] += t;
+            }
+        }
+        if (a.depth_pred && a.gt_depth && a.gt_depth_valid[r] > 0.f) { gtd += fabsf(a.depth_pred[r] - a.gt_depth[r]); gtd_cnt += 1.0; }
+    }
+    if (a.grad_theta)
+        for (uint32_t i = 0; i < a.G; ++i) {
+            const float *g1 = a.grad_theta + 3 * (size_t)i;
+            float ge[3] = {0, 0, 0}, gs1[3] = {0, 0, 0}, gs2[3] = {0, 0, 0};
+            if (a.w_eik > 0.f) eik += eikonal_term(g1, ge);
+            if (a.grad_theta_nei && a.w_smooth > 0.f) sm += smooth_term(g1, a.grad_theta_nei + 3 * (size_t)i, gs1, gs2);
+            const float ke = a.w_eik / (float)a.G, ks = a.w_smooth / (float)a.G;
+            for (int c = 0; c < 3; ++c) {
+                if (a.g_theta) a.g_theta[3 * (size_t)i + c] = ke * ge[c] + ks * gs1[c];
+                if (a.g_theta_nei) a.g_theta_nei[3 * (size_t)i + c] = ks * gs2[c];
+            }
+        }
+    const bool depth_on = a.depth_pred && a.depth_gt;
+    std::vector<float> scale(a.B, 0.f), shift(a.B, 0.f);
+    double mt = 0;
+    for (uint32_t b = 0; b < a.B; ++b) {
+        const double *f = fr.data() + 5 * b;
+        if (depth_on) scale_shift((float)f[0], (float)f[1], (float)f[2], (float)f[3], (float)f[4], &scale[b], &shift[b]);
+        mt += f[2];
+    }
+    const float m_total = (float)mt;
+    double mse = 0, reg = 0;
+    if (a.depth_pred)
+        for (uint32_t r = 0; r < a.R; ++r) {
+            float g = 0.f;
+            if (depth_on && m_total > 0.f) {
+                const uint32_t b = r / a.N, n = r - b * a.N;
+                const float s = scale[b], sh = shift[b];
+                auto msk = [&](uint32_t q) { return a.depth_mask_all ? 1.0f : maskf[q]; };
+                auto dif = [&](uint32_t q) { return msk(q) * ((s * a.depth_pred[q] + sh) - (a.depth_gt[q] * 50.0f + 0.5f)); };
+                const float m = msk(r);
+                const float res = (s * a.depth_pred[r] + sh) - (a.depth_gt[r] * 50.0f + 0.5f);
+                mse += (double)(m * res * res);
+                g = m * res * s / m_total;
+                const float d0 = m * res;
+                float sg = 0.f;
+                if (n > 0) sg += msk(r - 1) * m * sgnf(d0 - dif(r - 1));
+                if (n + 1 < a.N) {
+                    const float mm = m * msk(r + 1), dd = dif(r + 1) - d0;
+                    reg += (double)(mm * fabsf(dd));
+                    sg -= mm * sgnf(dd);
+                }
+                g += 0.5f * s * m * sg / m_total;
+                g *= a.w_depth;
+            }
+            if (a.gt_depth && gtd_cnt > 0 && a.gt_depth_valid[r] > 0.f) g += a.w_gt_depth * sgnf(a.depth_pred[r] - a.gt_depth[r]) / (float)gtd_cnt;
+            if (a.g_depth) a.g_depth[r] = g;
+        }
+    float depth = 0.f;
+    if (depth_on && m_total > 0.f) depth = (float)(mse / (2.0 * (double)m_total)) + 0.5f * (float)(reg / (double)m_total);
+    terms[NICER_LOSS_RGB] = a.rgb_pred ? (float)(rgb / (3.0 * (double)a.R)) : 0.f;
+    terms[NICER_LOSS_DEPTH] = depth;
+    terms[NICER_LOSS_GT_DEPTH] = a.gt_depth ? (float)(gtd / gtd_cnt) : 0.f;
+    terms[NICER_LOSS_NORMAL_L1] = a.normal_pred ? (float)(nl1 / (double)a.R) : 0.f;
+    terms[NICER_LOSS_NORMAL_COS] = a.normal_pred ? (float)(ncos / (double)a.R) : 0.f;
+    terms[NICER_LOSS_EIKONAL] = (a.grad_theta && a.w_eik > 0.f) ? (float)(eik / (double)a.G) : 0.f;
+    terms[NICER_LOSS_SMOOTH] = (a.grad_theta_nei && a.w_smooth > 0.f) ? (float)(sm / (double)a.G) : 0.f;
+    terms[NICER_LOSS_SUM] = a.w_rgb * terms[NICER_LOSS_RGB] + a.w_depth * terms[NICER_LOSS_DEPTH] +
+                            (a.gt_depth ? a.w_gt_depth * terms[NICER_LOSS_GT_DEPTH] : 0.f) +
+                            a.w_normal_l1 * terms[NICER_LOSS_NORMAL_L1] + a.w_normal_cos * terms[NICER_LOSS_NORMAL_COS] +
+                            a.w_eik * terms[NICER_LOSS_EIKONAL] + a.w_smooth * terms[NICER_LOSS_SMOOTH];
     return 0;
 }
