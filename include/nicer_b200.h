@@ -93,7 +93,9 @@ typedef struct {
  *   H0   [d_in][P]          the network input [x, PE(x), grid(x)] (operand of the layer-0 weight gradient, so that
  *                           the backward pass never re-reads the grid)
  */
-#define NICER_SDF_ONLY 1u        /* sdf only: no feat, no gradient, nothing saved (sampler pass, get_sdf_vals) */
+#define NICER_SDF_ONLY 1u        /* sdf only: no feat, no gradient, nothing saved (sampler pass, get_sdf_vals); H0, when
+                                    not NULL, is a [L*C][P] scratch for the grid features (gathered by a separate
+                                    high-occupancy kernel instead of inside the tensor-core kernel) */
 #define NICER_SDF_ACCUMULATE 2u  /* add into sdf/feat/grad instead of overwriting (coarse+fine sum, base_networks.py:40) */
 #define NICER_SDF_NO_FEAT 4u     /* gradient() path: sdf + gradient only (base_networks.py:195-206) */
 

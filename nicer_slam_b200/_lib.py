@@ -68,7 +68,7 @@ _SIGS = {
 
 _handle = None
 launch_count = 0          # kernels launched through this binding (bench.py's gpu_launches)
-_LAUNCHES = {"nicer_hash_encode_backward": 2, "nicer_sdf_forward": 2, "nicer_sdf_backward": 3, "nicer_color_backward": 2}
+_LAUNCHES = {"nicer_hash_encode_backward": 2, "nicer_sdf_forward": 2, "nicer_sdf_backward": 3, "nicer_color_backward": 2, "nicer_color_forward": 2}
 
 
 def _bind(h):

@@ -124,7 +124,14 @@ color_forward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, const
                 for (int k = 0; k < 33; ++k) H0[(size_t)k * Ps + p] = xvn[k];  // rows 0..32 of the input (for dW0)
             }
         }
-        {
+        if (H0) {
+            // grid features (and DYDX) were gathered by grid_encode_kernel into the grid rows of H0
+            float gf[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) gf[k] = (k < n_grid) ? __ldg(H0 + (size_t)(97 + k) * Ps + p) : 0.f;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) st_a8(t, c8, &gf[c8 * 8]);
+        } else {
             float u[3];
             to_unit(x, df, u);
 #pragma unroll
@@ -141,10 +148,6 @@ color_forward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, const
                         }
                     } else {
                         encode_level<C, false>(net.grid.table, lv[l], u, feat, dfeat);
-                    }
-                    if (H0 && valid) {
-#pragma unroll
-                        for (int c = 0; c < C; ++c) H0[(size_t)(97 + l * C + c) * Ps + p] = feat[c];
                     }
                 } else {
 #pragma unroll
@@ -353,6 +356,8 @@ color_backward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, cons
 bool tc_enabled();
 
 // 1: launched, 0: configuration not covered (caller falls back to the SIMT kernel), < 0: error
+int launch_grid_encode(const nicer_grid_t *g, const float *x, uint32_t P, float *F, float *DYDX, cudaStream_t st);
+
 int launch_color_forward_tc(const nicer_color_net_t *net, const float *x, const float *view, const float *normals, const float *feat_fm,
                             uint32_t P, float *rgb, float *A_fm, float *DYDX, float *H0, cudaStream_t st) {
     if (!tc_enabled() || net->n_hidden != 2 || net->multires_view != 4 || net->feature != 64) return 0;
@@ -362,6 +367,9 @@ int launch_color_forward_tc(const nicer_color_net_t *net, const float *x, const 
     const size_t smem = (size_t)pl.total_floats * sizeof(float);
     const uint32_t pairs = div_up(div_up(P, 128), 2);
     const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
+    if (H0 && has_grid) {      // gathers at full occupancy, into the grid rows of the saved network input
+        if (int e = launch_grid_encode(&net->grid, x, P, H0 + (size_t)97 * P, DYDX, st)) return e;
+    }
 #define LAUNCH(CC)                                                                                                        \
     do {                                                                                                                  \
         NICER_CUDA(cudaFuncSetAttribute(color_forward_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \

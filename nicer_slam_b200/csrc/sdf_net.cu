@@ -136,7 +136,7 @@ static int check_sdf_net(const nicer_sdf_net_t *net, const char *who) {
 }
 
 bool tc_enabled();
-int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, cudaStream_t st);
+int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *F, cudaStream_t st);
 int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
                           float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st);
 
@@ -169,7 +169,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_forward: n_hidden > 3 not built");
     // tensor-core (tcgen05, 3xTF32) path for the sdf-only pass; multires 6 + 64-wide layers is what it is built for
     if (sdf_only && tc_enabled() && net->multires == 6)
-        return launch_sdf_only_tc(net, x, P, flags, sdf, (cudaStream_t)stream);
+        return launch_sdf_only_tc(net, x, P, flags, sdf, H0, (cudaStream_t)stream);     // H0: optional [L*C][P] feature workspace
     if (!sdf_only && tc_enabled() && net->multires == 6)
         return launch_sdf_forward_tc(net, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX, H0, (cudaStream_t)stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);

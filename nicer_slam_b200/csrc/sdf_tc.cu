@@ -239,7 +239,8 @@ __device__ __forceinline__ void chunk_store(const Tile4 &t, const float *v) {
 template <int C>
 __global__ void __launch_bounds__(T4_THREADS, 2)
 sdf_only_tc4_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcSmemLayout lay, const float *__restrict__ X,
-                    uint32_t P, uint32_t accumulate, float *__restrict__ sdf) {
+                    uint32_t P, uint32_t accumulate, float *__restrict__ sdf, const float *__restrict__ F) {
+    // F != NULL: grid features [L*C][P] gathered beforehand by grid_encode_kernel (coalesced reads here)
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base_slot;
@@ -299,20 +300,25 @@ sdf_only_tc4_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcSme
             const uint32_t w0h = tc::smem_u32(smem + lay.w_hi[0]), w0l = tc::smem_u32(smem + lay.w_lo[0]);
             chunk_store<4>(t, h0);
             chunk_issue(t, w0h, w0l, 0, 4, false);           // runs while the grid levels are gathered
-            float u[3];
-            to_unit(x, df, u);
             h0[71] = 0.f;
+            if (F) {
 #pragma unroll
-            for (int l = 0; l < 32 / C; ++l) {
-                float feat[C], dummy[3][C];
-                if (l < L) {
-                    encode_level<C, false>(net.grid.table, lv[l], u, feat, dummy);
-                } else {
+                for (int k = 0; k < 32; ++k) h0[39 + k] = (k < L * C) ? __ldg(F + (size_t)k * P + p) : 0.f;
+            } else {
+                float u[3];
+                to_unit(x, df, u);
 #pragma unroll
-                    for (int c = 0; c < C; ++c) feat[c] = 0.f;
+                for (int l = 0; l < 32 / C; ++l) {
+                    float feat[C], dummy[3][C];
+                    if (l < L) {
+                        encode_level<C, false>(net.grid.table, lv[l], u, feat, dummy);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) feat[c] = 0.f;
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; ++c) h0[39 + l * C + c] = feat[c];
                 }
-#pragma unroll
-                for (int c = 0; c < C; ++c) h0[39 + l * C + c] = feat[c];
             }
             chunk_wait(t);
             chunk_store<4>(t, h0 + 32);
@@ -362,7 +368,10 @@ bool tc_enabled() {
 }
 void set_tc_enabled(int on) { g_tc_enabled = on ? 1 : 0; }
 
-int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, cudaStream_t st) {
+int launch_grid_encode(const nicer_grid_t *g, const float *x, uint32_t P, float *F, float *DYDX, cudaStream_t st);
+
+// F: optional [L*C][P] workspace; when given the gathers run in grid_encode_kernel at full occupancy first
+int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *F, cudaStream_t st) {
     TcSmemLayout lay = tc_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);
@@ -371,13 +380,16 @@ int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, u
     const uint32_t acc = (flags & NICER_SDF_ACCUMULATE) ? 1u : 0u;
     static const int tiles_per_sm = [] { const char *e = getenv("NICER_TC_TILES"); return (e && e[0] == '2') ? 2 : 4; }();
     if (tiles_per_sm == 4 && net->multires == 6) {
+        if (F) {
+            if (int e = launch_grid_encode(&net->grid, x, P, F, nullptr, st)) return e;
+        }
         const uint32_t pairs = div_up(tiles, 2);
         const uint32_t grid4 = pairs < (uint32_t)(2 * num_sms()) ? pairs : (uint32_t)(2 * num_sms());
 #define LAUNCH4(CC)                                                                                                  \
     do {                                                                                                             \
         NICER_CUDA(cudaFuncSetAttribute(sdf_only_tc4_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
                    "nicer_sdf_forward(tc4)");                                                                        \
-        sdf_only_tc4_kernel<CC><<<grid4, T4_THREADS, smem, st>>>(*net, ls, lay, x, P, acc, sdf);                     \
+        sdf_only_tc4_kernel<CC><<<grid4, T4_THREADS, smem, st>>>(*net, ls, lay, x, P, acc, sdf, F);                  \
     } while (0)
         switch (net->grid.C) {
             case 2: LAUNCH4(2); break;

@@ -172,6 +172,7 @@ template <int C>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 sdf_forward_tc_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
                       uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z, float *DYDX, float *H0) {
+    // H0 != NULL: its grid rows (and DYDX) were already written by grid_encode_kernel; this kernel adds the x / PE rows
     extern __shared__ __align__(16) float smem[];
     __shared__ TcfShared sh;
     LevelInfo *lv;
@@ -194,6 +195,11 @@ sdf_forward_tc_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
         float u[3];
         to_unit(x, df, u);
         // ---------------- network input -> A   (columns: [32 grid | 39 PE | pad])
+        float gf[32];
+        if (H0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) gf[k] = (k < L * C) ? __ldg(H0 + (size_t)(39 + k) * Ps + p) : 0.f;
+        }
         {
             float pe[48];
             pe[0] = x[0]; pe[1] = x[1]; pe[2] = x[2];
@@ -213,26 +219,28 @@ sdf_forward_tc_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
                 for (int k = 0; k < 39; ++k) H0[(size_t)k * Ps + p] = pe[k];
             }
         }
+        if (H0) {
+            // grid features were gathered by grid_encode_kernel into the grid rows of H0 (and DYDX): coalesced reads
 #pragma unroll
-        for (int l = 0; l < 32 / C; ++l) {
-            float feat[C], dfeat[3][C];
-            if (l < L) {
-                encode_level<C, true>(net.grid.table, lv[l], u, feat, dfeat);
-                if (valid) {
+            for (int c8 = 0; c8 < 4; ++c8) st_a8(t, c8, &gf[c8 * 8]);
+        } else {
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
+            for (int l = 0; l < 32 / C; ++l) {
+                float feat[C], dfeat[3][C];
+                if (l < L) {
+                    encode_level<C, true>(net.grid.table, lv[l], u, feat, dfeat);
+                    if (valid) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p] = dfeat[d][c];
-                    if (H0) {
+                        for (int d = 0; d < 3; ++d)
 #pragma unroll
-                        for (int c = 0; c < C; ++c) H0[(size_t)(39 + l * C + c) * Ps + p] = feat[c];
+                            for (int c = 0; c < C; ++c) DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p] = dfeat[d][c];
                     }
-                }
-            } else {
+                } else {
 #pragma unroll
-                for (int c = 0; c < C; ++c) feat[c] = 0.f;
+                    for (int c = 0; c < C; ++c) feat[c] = 0.f;
+                }
+                st_a_small<C>(t, l * C, feat);
             }
-            st_a_small<C>(t, l * C, feat);
         }
         // ---------------- hidden layers
         float s_out = bl_sdf;
@@ -386,6 +394,8 @@ sdf_forward_tc_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const T
     tile_teardown(sh);
 }
 
+int launch_grid_encode(const nicer_grid_t *g, const float *x, uint32_t P, float *F, float *DYDX, cudaStream_t st);
+
 int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
                           float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
@@ -393,6 +403,9 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
     const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
     const TcfPlan pa = plan_a(net), pb = plan_b(net);
     const size_t smem_a = (size_t)pa.total_floats * sizeof(float), smem_b = (size_t)pb.total_floats * sizeof(float);
+    if (H0) {       // gathers at full occupancy, into the grid rows of the saved network input
+        if (int e = launch_grid_encode(&net->grid, x, P, H0 + (size_t)39 * P, DYDX, st)) return e;
+    }
 #define LAUNCH(CC)                                                                                                      \
     do {                                                                                                                \
         NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tc_a_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a), \

@@ -266,13 +266,15 @@ def sdf_values(x, nets, out=None):
     x = _c(x.detach())
     P = x.shape[0]
     sdf = out if out is not None else torch.empty(P, device=x.device)
+    # scratch for the grid features of one net at a time (the gathers run in their own high-occupancy kernel)
+    rows = max(meta.grid.L * meta.grid.C for meta, _t, _o, _w in nets)
+    feat_ws = torch.empty(rows, P, device=x.device) if x.is_cuda else None
     for i, (meta, table, offsets, wb) in enumerate(nets):
         wb = tuple(_c(t.detach()) for t in wb)
         net = _sdf_struct(meta, table.detach(), offsets, wb)
         flags = F_SDF_ONLY | (F_ACCUMULATE if i > 0 else 0)
         check(lib().nicer_sdf_forward(C.byref(net), ptr(x), P, flags, ptr(sdf), None, None, None, None, None,
-                                      None, stream()), "nicer_sdf_forward")
-        _lib.launch_count -= 1      # the sdf-only pass is one kernel (the full forward is two)
+                                      ptr(feat_ws), stream()), "nicer_sdf_forward")
     return sdf.view(P, 1)
 
 
