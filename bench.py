@@ -276,10 +276,12 @@ def cpu_reference_step(rays, frames, seed, color_logmap, threads):
 
 
 def time_cpu(rays, frames, steps, warmup, color_logmap=19):
-    threads = os.cpu_count() or 1
+    # the oracle's torch ops are small ([rays*98, 64] matrices): more than ~16 threads only adds scheduling overhead
+    # (measured on the 128-core GPU box: 350 samples/s with 128 threads), so the baseline uses min(cores, 16)
+    threads = min(os.cpu_count() or 1, 16)
+    if warmup:      # warm-up on a 16-ray step (loads the oracle library, spins up the thread pool): a few seconds
+        cpu_reference_step(frames, frames, 0, color_logmap, threads)()
     step = cpu_reference_step(rays, frames, 0, color_logmap, threads)
-    for _ in range(warmup):
-        step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
@@ -311,7 +313,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cpu_rays, cpu_frames = 256, 16
+        cpu_rays, cpu_frames = 2048, 16
         steps = min(args.steps, 3)
         val, dt, threads = time_cpu(cpu_rays, cpu_frames, steps, min(args.warmup, 1))
         sample = f"{cpu_rays} of the {args.rays} rays per step ({cpu_frames} frames x {cpu_rays // cpu_frames} px), color grid 2^19/level, {steps} steps"
@@ -416,9 +418,9 @@ def main():
         extra = kernel_breakdown(step, dev)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, threads = time_cpu(256, 16, 1, 1)
+        v, dt, threads = time_cpu(2048, 16, 1, 1)
         cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
-               "sample": "256 of the 4096 rays of one step (16 frames x 16 px), color grid 2^19/level, 1 timed step after 1 warm-up"}
+               "sample": "2048 of the 4096 rays of one step (16 frames x 128 px), color grid 2^19/level, 1 timed step after a 16-ray warm-up"}
     if rank == 0:
         peaks = _peaks()
         line = {"metric": "ray-samples/sec fwd+bwd", "value": value, "unit": "ray-samples/s", "n_gpus": world,
@@ -494,7 +496,21 @@ def kernel_breakdown(step, dev):
     U = step.rays * N_EVAL
     xu = (torch.rand(U, 3, device=dev) * 2 - 1) * 0.9
     args = fine.fused_args()
-    t_dom = timed(lambda: ops.sdf_values(xu, [args]))
+    # the sampler pass of one net is two kernels (grid_encode_kernel, then the tcgen05 MLP kernel): fill the feature scratch
+    # once, then time the MLP kernel alone through the C ABI (NICER_SDF_FEATURES_READY skips the gather launch)
+    import ctypes as C
+    from nicer_slam_b200 import _lib
+    meta, table, off, wb = args
+    wb = tuple(t.detach().contiguous() for t in wb)
+    net = ops._sdf_struct(meta, table.detach(), off, wb)
+    ws = torch.empty(meta.grid.L * meta.grid.C, U, device=dev)
+    sdf_out = torch.empty(U, device=dev)
+
+    def mlp_only(flags):
+        _lib.check(_lib.lib().nicer_sdf_forward(C.byref(net), _lib.ptr(xu), U, flags, _lib.ptr(sdf_out), None, None, None, None,
+                                                None, _lib.ptr(ws), _lib.stream()), "nicer_sdf_forward")
+    mlp_only(ops.F_SDF_ONLY)
+    t_dom = timed(lambda: mlp_only(ops.F_SDF_ONLY | 8))
     dims = [71, 64, 64, 64]
     flop_pt = 2 * (sum(dims[i] * dims[i + 1] for i in range(3)) + 64)       # 3 hidden layers + the sdf output row
     peaks = _peaks()
@@ -503,7 +519,7 @@ def kernel_breakdown(step, dev):
     tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    res["roofline"] = {"bound": "tensor", "kernel": "sdf_only_tc_kernel<4> (fine SDF net, sampler pass, tcgen05 3xTF32)",
+    res["roofline"] = {"bound": "tensor", "kernel": "sdf_only_tc4_kernel<4> (fine SDF net MLP, sampler pass, tcgen05 3xTF32)",
                        "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                        "traffic": traffic, "flop_per_point": flop_pt, "points_per_launch": U, "ms_per_launch": t_dom,
                        "note": "algorithmic fp32 FLOPs; the kernel executes 3 tf32 MMAs per product (3xTF32) at half the bf16 "

@@ -96,6 +96,7 @@ typedef struct {
 #define NICER_SDF_ONLY 1u        /* sdf only: no feat, no gradient, nothing saved (sampler pass, get_sdf_vals); H0, when
                                     not NULL, is a [L*C][P] scratch for the grid features (gathered by a separate
                                     high-occupancy kernel instead of inside the tensor-core kernel) */
+#define NICER_SDF_FEATURES_READY 8u /* with NICER_SDF_ONLY: H0 already holds the grid features of x (skip the gather kernel) */
 #define NICER_SDF_ACCUMULATE 2u  /* add into sdf/feat/grad instead of overwriting (coarse+fine sum, base_networks.py:40) */
 #define NICER_SDF_NO_FEAT 4u     /* gradient() path: sdf + gradient only (base_networks.py:195-206) */
 

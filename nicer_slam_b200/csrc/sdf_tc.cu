@@ -380,7 +380,7 @@ int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, u
     const uint32_t acc = (flags & NICER_SDF_ACCUMULATE) ? 1u : 0u;
     static const int tiles_per_sm = [] { const char *e = getenv("NICER_TC_TILES"); return (e && e[0] == '2') ? 2 : 4; }();
     if (tiles_per_sm == 4 && net->multires == 6) {
-        if (F) {
+        if (F && !(flags & NICER_SDF_FEATURES_READY)) {
             if (int e = launch_grid_encode(&net->grid, x, P, F, nullptr, st)) return e;
         }
         const uint32_t pairs = div_up(tiles, 2);
