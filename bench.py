@@ -490,8 +490,26 @@ def kernel_breakdown(step, dev):
         rgb.backward(torch.ones_like(rgb))
     t_col = timed(color_fb)
     res["core_full"] = {"ms": t_c + t_f + t_col, "ray_samples_per_s": P / ((t_c + t_f + t_col) * 1e-3)}
-    # ---- roofline entry: the dominant kernel of the step (profiles/r01_launches_summary.csv) is the tcgen05 sdf-only
-    # kernel of the fine network in the sampler pass (U = rays x 640 points per launch)
+    # ---- roofline entries.  The largest share of the step (profiles/r01_launches_summary.csv) is the weight-gradient
+    # contraction outer_accum_tc_kernel (25 launches): C[64,N] += A[64][P] B[N][P]^T, 2*64*N*P flops over (64+N)*P*4 bytes
+    # = 16.8 FLOP/B at N = 64 -> HBM-bound.  Timed here on the main-pass hidden-layer shape (M = N = 64, P = rays x S).
+    peaks = _peaks()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    Aw, Bw = torch.randn(64, P, device=dev), torch.randn(64, P, device=dev)
+    Cw, bw = torch.zeros(64, 64, device=dev), torch.zeros(64, device=dev)
+    t_w = timed(lambda: ops.outer_accum(Aw, Bw, Cw, bw), n=10)
+    bytes_w = (64 + 64) * P * 4
+    ach_w = bytes_w / (t_w * 1e-3) / 1e9
+    res["roofline"] = {"bound": "hbm", "kernel": "outer_accum_tc_kernel (weight-gradient contraction, M=N=64, P=rays*S; 25 launches "
+                       "= the largest share of the step)", "achieved": ach_w, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": ach_w / peaks["hbm_gbs"], "traffic": traffic.get("dram_bytes_per_launch"),
+                       "algorithmic_bytes_per_launch": bytes_w, "bytes_per_ray_sample": (64 + 64) * 4, "ms_per_launch": t_w,
+                       "note": "peak = measured copy bandwidth (burst); the kernel is paced by tcgen05.mma issue (24 per 64-sample "
+                               "stage at ~102 cycles each, scripts/mma_bench.cu), not by DRAM"}
+    # second entry: the largest tensor-core kernel, the sampler pass of the fine SDF net (U = rays x 640 points per launch)
     fine = m.implicit_network.fine
     U = step.rays * N_EVAL
     xu = (torch.rand(U, 3, device=dev) * 2 - 1) * 0.9
@@ -513,17 +531,14 @@ def kernel_breakdown(step, dev):
     t_dom = timed(lambda: mlp_only(ops.F_SDF_ONLY | 8))
     dims = [71, 64, 64, 64]
     flop_pt = 2 * (sum(dims[i] * dims[i + 1] for i in range(3)) + 64)       # 3 hidden layers + the sdf output row
-    peaks = _peaks()
     ach = U * flop_pt / (t_dom * 1e-3) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    res["roofline"] = {"bound": "tensor", "kernel": "sdf_only_tc4_kernel<4> (fine SDF net MLP, sampler pass, tcgen05 3xTF32)",
-                       "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                       "traffic": traffic, "flop_per_point": flop_pt, "points_per_launch": U, "ms_per_launch": t_dom,
-                       "note": "algorithmic fp32 FLOPs; the kernel executes 3 tf32 MMAs per product (3xTF32) at half the bf16 "
-                               "rate, so the tensor pipe is ~6x busier than this fraction says; peak = measured dense bf16 (burst)"}
+    res["roofline_tensor"] = {"bound": "tensor", "kernel": "sdf_only_tc4_kernel<4> (fine SDF net MLP, sampler pass, tcgen05 3xTF32)",
+                              "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                              "traffic": (traffic.get("tensor_kernel") or {}).get("dram_bytes_per_launch"),
+                              "flop_per_point": flop_pt, "points_per_launch": U, "ms_per_launch": t_dom,
+                              "note": "algorithmic fp32 FLOPs; the kernel executes 3 tf32 MMAs per product (3xTF32) with N = 64, and a "
+                                      "tcgen05.mma costs ~102 cycles for any N <= 128 (scripts/mma_bench.cu), so a 64-wide layer can use "
+                                      "at most 1/3 of the tf32 rate = 1/6 of this bf16 peak; peak = measured dense bf16 (burst)"}
     return res
 
 
