@@ -208,6 +208,18 @@ typedef struct {
 } nicer_loss_t;
 int nicer_slam_loss(const nicer_loss_t *args, double *acc, float *maskf, float *terms, void *stream);
 
+/* ---- photometric warp sampling (model/network.py:167-279): every pixel of every frame i, lifted with its rendered depth,
+ * is projected into every frame t of the batch and t's colour image is sampled bilinearly (grid_sample, align_corners).
+ *   depth [B*N], dirs [B*N*pp,3] and loc [B,3] (rays of the patch pixels), w2c [B,4,4], K [B,4,4], img [B,H,W,3]
+ *   -> sampled [B(t)][B*N*pp][3], mask [B(t)][B*N*pp] (uint8: inside the image and in front of the camera)
+ * backward: g_sampled -> g_dirs (written), g_depth / g_loc / g_w2c (accumulated with atomics: must arrive zeroed). */
+int nicer_warp_sample(const float *depth, const float *dirs, const float *loc, const float *w2c, const float *K,
+                      const float *img, uint32_t B, uint32_t N, uint32_t pp, uint32_t H, uint32_t W, float *sampled,
+                      uint8_t *mask, void *stream);
+int nicer_warp_sample_backward(const float *depth, const float *dirs, const float *loc, const float *w2c, const float *K,
+                               const float *img, uint32_t B, uint32_t N, uint32_t pp, uint32_t H, uint32_t W,
+                               const float *g_sampled, float *g_depth, float *g_dirs, float *g_loc, float *g_w2c, void *stream);
+
 /* ---- camera / ray helpers (one kernel each; the reference runs them as ~200 elementwise kernels per iteration)
  * nicer_pose_from_cam7            <- get_camera_from_tensor / quad2rotation   utils/general.py:52-100
  *   cam7 [B,7] (quaternion w,x,y,z un-normalised, translation) -> pose [B,4,4] row-major c2w

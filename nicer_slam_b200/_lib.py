@@ -58,6 +58,8 @@ _SIGS = {
     "nicer_voxel_count": [_fp, _u32, _fp, _u32, _fp],
     "nicer_set_tensor_cores": [C.c_int],
     "nicer_slam_loss": [C.POINTER(LossT), _fp, _fp, _fp, _fp],
+    "nicer_warp_sample": [_fp] * 6 + [_u32] * 5 + [_fp, _fp, _fp],
+    "nicer_warp_sample_backward": [_fp] * 6 + [_u32] * 5 + [_fp] * 6,
     "nicer_pose_from_cam7": [_fp, _u32, _fp, _fp],
     "nicer_pose_from_cam7_backward": [_fp, _fp, _u32, _fp, _fp],
     "nicer_camera_rays": [_fp, _fp, _fp, _u32, _u32, _fp, _fp, _fp],

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", f) for f in
-       ("api.cu", "hash_encode.cu", "sdf_net.cu", "sdf_tc.cu", "sdf_tc_full.cu", "color_net.cu", "color_tc.cu", "outer_accum.cu", "outer_accum_tc.cu", "composite.cu", "grid_scatter.cu", "geometry.cu", "loss.cu", "grid_encode.cu")]
+       ("api.cu", "hash_encode.cu", "sdf_net.cu", "sdf_tc.cu", "sdf_tc_full.cu", "color_net.cu", "color_tc.cu", "outer_accum.cu", "outer_accum_tc.cu", "composite.cu", "grid_scatter.cu", "geometry.cu", "loss.cu", "grid_encode.cu", "warp.cu")]
 OUT = os.path.join(HERE, "libnicer_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-shared"]

@@ -2,7 +2,7 @@
 // Both operands are the feature-major buffers of the fused backward kernels, i.e. already K-major with K = samples.
 // The product is computed transposed, D^T[N (128 TMEM lanes)][M (64 columns)] = Bop * Aop^T with the B rows as the
 // M=128 operand (rows >= N are zero, row N is all ones so that D^T[N][m] = rowsum(A)[m] comes for free) and the A rows
-// as the N=64 operand; both operands go through shared memory in the UMMA K-major no-swizzle layout as (hi, lo) pairs.
+// as the N operand; both operands go through shared memory in the UMMA K-major no-swizzle layout as (hi, lo) pairs.
 // Split-K over CTAs (2 CTAs/SM, 64 samples per stage, next stage's global loads prefetched into registers while the
 // MMAs of the current one run), one red.global.add per output element per CTA at the end.
 #include "common.cuh"
@@ -20,7 +20,10 @@ constexpr int OT_PER_WARP = OT_MAX_UNITS / (OT_THREADS / 32);   // 12
 
 struct OtSmem {
     float bhi[OT_CH * OT_BROWS * 4], blo[OT_CH * OT_BROWS * 4];   // 32 KB each
-    float ahi[OT_CH * OT_AROWS * 4], alo[OT_CH * OT_AROWS * 4];   // 16 KB each
+    // A rows as ONE 128-row operand per chunk: rows [0,64) hold the hi halves, rows [64,128) the lo halves, so that
+    // B_hi x [A_hi ; A_lo] is a single N = 128 MMA (a tcgen05.mma costs the same ~102 cycles for N = 64 and N = 128,
+    // scripts/mma_bench.cu): 2 MMAs per K-step instead of 3
+    float acomb[OT_CH * 2 * OT_AROWS * 4];                        // 32 KB
 };
 
 __global__ void __launch_bounds__(OT_THREADS, 2)
@@ -44,7 +47,7 @@ outer_accum_tc_kernel(const float *__restrict__ A, uint32_t lda, uint32_t M, con
         for (int i = tid; i < OT_CH * 4; i += OT_THREADS) sm.bhi[((i >> 2) * OT_BROWS + N) * 4 + (i & 3)] = 1.0f;   // exact in tf32
     }
     if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, 64);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 128);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -86,9 +89,8 @@ outer_accum_tc_kernel(const float *__restrict__ A, uint32_t lda, uint32_t M, con
                 float4 h, l;
                 h.x = tc::tf32_hi(v.x); h.y = tc::tf32_hi(v.y); h.z = tc::tf32_hi(v.z); h.w = tc::tf32_hi(v.w);
                 l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                const uint32_t rows = isA ? OT_AROWS : OT_BROWS;
-                float *dh = (isA ? sm.ahi : sm.bhi) + ((size_t)c * rows + r) * 4;
-                float *dl = (isA ? sm.alo : sm.blo) + ((size_t)c * rows + r) * 4;
+                float *dh = isA ? sm.acomb + ((size_t)c * 2 * OT_AROWS + r) * 4 : sm.bhi + ((size_t)c * OT_BROWS + r) * 4;
+                float *dl = isA ? sm.acomb + ((size_t)c * 2 * OT_AROWS + OT_AROWS + r) * 4 : sm.blo + ((size_t)c * OT_BROWS + r) * 4;
                 *reinterpret_cast<float4 *>(dh) = h;
                 *reinterpret_cast<float4 *>(dl) = l;
             }
@@ -104,17 +106,17 @@ outer_accum_tc_kernel(const float *__restrict__ A, uint32_t lda, uint32_t M, con
         __syncthreads();
         if (tid == 0) {
             tc::fence_after_sync();
-            constexpr uint32_t IDESC = tc::idesc_tf32(128, 64);
-            const uint32_t bh = tc::smem_u32(sm.bhi), bl = tc::smem_u32(sm.blo), ah = tc::smem_u32(sm.ahi), al = tc::smem_u32(sm.alo);
+            constexpr uint32_t IDESC128 = tc::idesc_tf32(128, 2 * OT_AROWS), IDESC64 = tc::idesc_tf32(128, OT_AROWS);
+            const uint32_t bh = tc::smem_u32(sm.bhi), bl = tc::smem_u32(sm.blo), ac = tc::smem_u32(sm.acomb);
 #pragma unroll
             for (int ks = 0; ks < OT_KC / 8; ++ks) {
                 const uint64_t dbh = tc::smem_desc(bh + ks * 2 * OT_BROWS * 16, OT_BROWS * 16, 128);
                 const uint64_t dbl = tc::smem_desc(bl + ks * 2 * OT_BROWS * 16, OT_BROWS * 16, 128);
-                const uint64_t dah = tc::smem_desc(ah + ks * 2 * OT_AROWS * 16, OT_AROWS * 16, 128);
-                const uint64_t dal = tc::smem_desc(al + ks * 2 * OT_AROWS * 16, OT_AROWS * 16, 128);
-                tc::mma_tf32_ss(tmem, dbh, dah, IDESC, (first && ks == 0) ? 0u : 1u);
-                tc::mma_tf32_ss(tmem, dbl, dah, IDESC, 1u);
-                tc::mma_tf32_ss(tmem, dbh, dal, IDESC, 1u);
+                // the combined operand (128 rows per chunk); its first 64 rows alone are A_hi (same chunk stride)
+                const uint64_t dac = tc::smem_desc(ac + ks * 2 * (2 * OT_AROWS) * 16, 2 * OT_AROWS * 16, 128);
+                // columns [0,64) += B_hi A_hi^T, columns [64,128) += B_hi A_lo^T ; then columns [0,64) += B_lo A_hi^T
+                tc::mma_tf32_ss(tmem, dbh, dac, IDESC128, (first && ks == 0) ? 0u : 1u);
+                tc::mma_tf32_ss(tmem, dbl, dac, IDESC64, 1u);
             }
             tc::mma_commit(&bar);
         }
@@ -131,11 +133,13 @@ outer_accum_tc_kernel(const float *__restrict__ A, uint32_t lda, uint32_t M, con
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
-            float v[8];
+            float v[8], w[8];
             tc::tmem_ld8(lane_base + c8 * 8, v);
+            tc::tmem_ld8(lane_base + OT_AROWS + c8 * 8, w);
             tc::wait_ld();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
+                v[i] += w[i];
                 const uint32_t m = c8 * 8 + i;
                 if (m < M) {
                     if (n < N) atomicAdd(&C[(size_t)m * ldc + n], v[i]);
@@ -146,7 +150,7 @@ outer_accum_tc_kernel(const float *__restrict__ A, uint32_t lda, uint32_t M, con
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+    if (warp == 0) tc::tmem_dealloc(tmem, 128);
 }
 
 bool tc_enabled();

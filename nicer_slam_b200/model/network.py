@@ -185,20 +185,8 @@ class SLAMNetwork(nn.Module):
             pp = ps * ps
             uv_patch = uv2patch(uv, ps).reshape(bs, -1, 2)
             dirs_p, loc_p = rend_util.get_camera_params(uv_patch, pose, intrinsics)
-            pts = loc_p[:, None, None, :] + depth * dirs_p.reshape(bs, -1, pp, 3)
-            pts = pts.reshape(-1, 3).permute(1, 0)                                  # [3, bs*N*pp]
-            cam_pts = w2c[:, :3, :3] @ pts + w2c[:, :3, 3:]                          # [bs(target), 3, bs*N*pp]
-            proj = (K3 @ cam_pts).permute(0, 2, 1).reshape(bs, bs, -1, pp, 3)        # (target, reference, N, pp, 3)
-            t_depth = proj[..., 2:]
-            t_uv = proj[..., :2] / (t_depth + 1e-8)
-            t_uv = torch.stack([t_uv[..., 0] / W, t_uv[..., 1] / H], -1) * 2 - 1.0
-            t_uv = t_uv.reshape(bs, -1, 1, 2)
-            t_depth = t_depth.reshape(bs, -1, 1)
-            sampled = F.grid_sample(full_rgb.permute(0, 3, 1, 2), t_uv, mode="bilinear", padding_mode="zeros",
-                                    align_corners=True)
-            sampled = sampled.reshape(bs, 3, bs, -1, pp).permute(0, 2, 3, 4, 1)
-            s_mask = ((t_uv[..., 0] > -1) & (t_uv[..., 0] < 1) & (t_uv[..., 1] > -1) & (t_uv[..., 1] < 1)
-                      & (t_depth > 0)).reshape(bs, bs, -1, pp)
+            # lift with the rendered depth, project into every frame, bilinear lookup, in-image / in-front mask: one kernel
+            sampled, s_mask = ops.WarpSampleFn.apply(depth.reshape(bs, -1), dirs_p, loc_p, w2c, intrinsics, full_rgb, pp)
             # ground-truth colour / depth of the patch pixels in their own frame (1 where outside the image)
             u, v = uv_patch[..., 0], uv_patch[..., 1]
             inside = (0 <= u) & (0 <= v) & (u < W) & (v < H)

@@ -602,3 +602,41 @@ class SlamLossFn(torch.autograd.Function):
         g = ctx.grads
         return tuple((g[n] * g_sum if g[n] is not None else None)
                      for n in ("g_rgb", "g_depth", "g_normal", "g_theta", "g_theta_nei")) + (None,)
+
+
+# --------------------------------------------------------------------------------------------- warp sampling
+class WarpSampleFn(torch.autograd.Function):
+    """(depth [B,N], dirs_p [B,N*pp,3], loc_p [B,3], w2c [B,4,4], K [B,4,4], full_rgb [B,H,W,3]) ->
+    (sampled [B,B,N,pp,3], in-image mask [B,B,N,pp] bool)   -- the projection + grid_sample core of the warp block
+    (network.py:167-279); differentiable w.r.t. depth, the patch rays and the world-to-camera matrices."""
+
+    @staticmethod
+    def forward(ctx, depth, dirs_p, loc_p, w2c, K, full_rgb, pp):
+        depth, dirs_p, loc_p = _c(depth.detach().float()), _c(dirs_p.detach()), _c(loc_p.detach())
+        w2c, K, img = _c(w2c.detach()), _c(K.detach()), _c(full_rgb.detach())
+        B, N = depth.shape[0], depth.shape[1]
+        H, W = img.shape[1], img.shape[2]
+        E = B * N * pp
+        sampled = torch.empty(B, E, 3, device=depth.device)
+        mask = torch.empty(B, E, dtype=torch.uint8, device=depth.device)
+        check(lib().nicer_warp_sample(ptr(depth), ptr(dirs_p), ptr(loc_p), ptr(w2c), ptr(K), ptr(img), B, N, pp, H, W,
+                                      ptr(sampled), C.c_void_p(mask.data_ptr()), stream()), "nicer_warp_sample")
+        ctx.save_for_backward(depth, dirs_p, loc_p, w2c, K, img)
+        ctx.dims = (B, N, pp, H, W)
+        m = mask.bool().reshape(B, B, N, pp)
+        ctx.mark_non_differentiable(m)
+        return sampled.reshape(B, B, N, pp, 3), m
+
+    @staticmethod
+    def backward(ctx, g_sampled, _g_mask):
+        depth, dirs_p, loc_p, w2c, K, img = ctx.saved_tensors
+        B, N, pp, H, W = ctx.dims
+        dev = depth.device
+        g_depth = torch.zeros(B, N, device=dev)
+        g_dirs = torch.empty_like(dirs_p)
+        g_loc = torch.zeros(B, 3, device=dev)
+        g_w2c = torch.zeros(B, 4, 4, device=dev)
+        check(lib().nicer_warp_sample_backward(ptr(depth), ptr(dirs_p), ptr(loc_p), ptr(w2c), ptr(K), ptr(img), B, N, pp, H, W,
+                                               ptr(_c(g_sampled)), ptr(g_depth), ptr(g_dirs), ptr(g_loc), ptr(g_w2c), stream()),
+              "nicer_warp_sample_backward")
+        return g_depth, g_dirs, g_loc, g_w2c, None, None, None

@@ -12,6 +12,7 @@
 #include "../../nicer_slam_b200/csrc/color_sample.cuh"
 #include "../../nicer_slam_b200/csrc/geometry_math.cuh"
 #include "../../nicer_slam_b200/csrc/loss_math.cuh"
+#include "../../nicer_slam_b200/csrc/warp_math.cuh"
 #include "../../nicer_slam_b200/csrc/composite_math.cuh"
 
 using namespace nicer;
@@ -476,5 +477,55 @@ extern "C" int nicer_slam_loss(const nicer_loss_t *args, double *, float *maskf,
                             (a.gt_depth ? a.w_gt_depth * terms[NICER_LOSS_GT_DEPTH] : 0.f) +
                             a.w_normal_l1 * terms[NICER_LOSS_NORMAL_L1] + a.w_normal_cos * terms[NICER_LOSS_NORMAL_COS] +
                             a.w_eik * terms[NICER_LOSS_EIKONAL] + a.w_smooth * terms[NICER_LOSS_SMOOTH];
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------- warp sampling
+extern "C" int nicer_warp_sample(const float *depth, const float *dirs, const float *loc, const float *w2c, const float *K,
+                                 const float *img, uint32_t B, uint32_t N, uint32_t pp, uint32_t H, uint32_t W, float *sampled,
+                                 uint8_t *mask, void *) {
+    const uint32_t E = B * N * pp;
+    for (uint32_t e = 0; e < E; ++e) {
+        const uint32_t i = e / (N * pp), ray = e / pp;
+        float pts[3];
+        for (int a = 0; a < 3; ++a) pts[a] = loc[3 * i + a] + depth[ray] * dirs[3 * (size_t)e + a];
+        for (uint32_t t = 0; t < B; ++t) {
+            const WarpProj pr = warp_project(pts, w2c + 16 * t, K + 16 * t, (float)W, (float)H);
+            const size_t o = (size_t)t * E + e;
+            bilinear3(img + (size_t)t * H * W * 3, (int)H, (int)W, pr.nu, pr.nv, sampled + 3 * o, nullptr, nullptr, nullptr);
+            mask[o] = (pr.nu > -1.0f && pr.nu < 1.0f && pr.nv > -1.0f && pr.nv < 1.0f && pr.proj[2] > 0.f) ? 1 : 0;
+        }
+    }
+    return 0;
+}
+extern "C" int nicer_warp_sample_backward(const float *depth, const float *dirs, const float *loc, const float *w2c, const float *K,
+                                          const float *img, uint32_t B, uint32_t N, uint32_t pp, uint32_t H, uint32_t W,
+                                          const float *g_sampled, float *g_depth, float *g_dirs, float *g_loc, float *g_w2c, void *) {
+    const uint32_t E = B * N * pp;
+    for (uint32_t e = 0; e < E; ++e) {
+        const uint32_t i = e / (N * pp), ray = e / pp;
+        const float d = depth[ray];
+        float dir[3], pts[3], gp[3] = {0, 0, 0};
+        for (int a = 0; a < 3; ++a) { dir[a] = dirs[3 * (size_t)e + a]; pts[a] = loc[3 * i + a] + d * dir[a]; }
+        for (uint32_t t = 0; t < B; ++t) {
+            const float *Wt = w2c + 16 * t, *Kt = K + 16 * t;
+            const WarpProj pr = warp_project(pts, Wt, Kt, (float)W, (float)H);
+            const float *g = g_sampled + 3 * ((size_t)t * E + e);
+            float out[3], dnu, dnv;
+            bilinear3(img + (size_t)t * H * W * 3, (int)H, (int)W, pr.nu, pr.nv, out, g, &dnu, &dnv);
+            const float ax = dnu * 2.0f / (float)W, ay = dnv * 2.0f / (float)H;
+            const float gproj[3] = {ax / pr.zden, ay / pr.zden, -(ax * pr.proj[0] + ay * pr.proj[1]) / (pr.zden * pr.zden)};
+            float gcam[3];
+            for (int c = 0; c < 3; ++c) gcam[c] = Kt[c] * gproj[0] + Kt[4 + c] * gproj[1] + Kt[8 + c] * gproj[2];
+            for (int c = 0; c < 3; ++c) gp[c] += Wt[c] * gcam[0] + Wt[4 + c] * gcam[1] + Wt[8 + c] * gcam[2];
+            for (int a = 0; a < 3; ++a) {
+                for (int c = 0; c < 3; ++c) g_w2c[16 * t + 4 * a + c] += gcam[a] * pts[c];
+                g_w2c[16 * t + 4 * a + 3] += gcam[a];
+            }
+        }
+        for (int a = 0; a < 3; ++a) { g_dirs[3 * (size_t)e + a] = d * gp[a]; g_loc[3 * i + a] += gp[a]; }
+        g_depth[ray] += gp[0] * dir[0] + gp[1] * dir[1] + gp[2] * dir[2];
+    }
     return 0;
 }
