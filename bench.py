@@ -335,6 +335,8 @@ def main():
     from nicer_slam_b200 import parallel
 
     step = build_step(args.rays, args.frames, args.color_logmap, dev, seed=rank)
+    if world > 1 and os.environ.get("NICER_OVERLAP_ALLREDUCE", "1") == "1":
+        parallel.overlap_grid_allreduce(step.model)     # the 1 GB color-grid all-reduce runs under the SDF backward
     P = args.rays * S_MAIN
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)   # 192 MiB > 126 MB L2
 

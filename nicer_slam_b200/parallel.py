@@ -95,6 +95,27 @@ def gather_ground_truth(gt):
     return res
 
 
+_EARLY = {}     # id(param) -> async work handle of an all-reduce started by the post-accumulate hook of this backward
+
+
+def overlap_grid_allreduce(model, big=1 << 20):
+    """Start the all-reduce of every big (grid) gradient the moment autograd has finished accumulating it, so that it
+    runs under the rest of the backward pass instead of after it: the 1 GB color-grid gradient is final right after the
+    color network's backward, with the whole SDF backward (tangent / reverse kernels, weight gradients) still to come.
+    allreduce_gradients() then only waits for those handles.  Call once after building the model (no-op for 1 rank)."""
+    if world() == 1:
+        return []
+    hooks = []
+    for p in model.parameters():
+        if p.requires_grad and p.numel() >= big:
+            def hook(param):
+                g = param.grad
+                if g is not None and g.is_contiguous():
+                    _EARLY[id(param)] = dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True)
+            hooks.append(p.register_post_accumulate_grad_hook(hook))
+    return hooks
+
+
 def allreduce_gradients(model, extra=(), average=False, big=1 << 20):
     """Sum every parameter gradient (+ extra leaf tensors, e.g. the pose 7-vectors) over the ranks: the small ones
     (MLP weights, poses) travel in ONE flat buffer, the grid gradients (>= `big` elements; the color grid is 1 GB) are
@@ -108,7 +129,12 @@ def allreduce_gradients(model, extra=(), average=False, big=1 << 20):
     for t in tensors:
         if t.grad is None:
             t.grad = torch.zeros_like(t)
-        if t.grad.numel() >= big and t.grad.is_contiguous():
+        early = _EARLY.pop(id(t), None)
+        if early is not None:
+            early.wait()                 # started by overlap_grid_allreduce's hook during the backward pass
+            if average:
+                t.grad.div_(w)
+        elif t.grad.numel() >= big and t.grad.is_contiguous():
             dist.all_reduce(t.grad, op=dist.ReduceOp.SUM)
             if average:
                 t.grad.div_(w)

@@ -74,6 +74,11 @@ def _step(model, fx, meta, sharded):
     return out, lo, cam7.grad, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}, model.voxels.clone()
 
 
+def parallel_mod():
+    from nicer_slam_b200 import parallel
+    return parallel
+
+
 def _worker(rank, world, port, ret):
     sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, HERE)
     import warnings
@@ -88,6 +93,9 @@ def _worker(rank, world, port, ret):
         model, _ = gu.build_model()
         out1, lo1, gcam1, g1, vox1 = _step(model, fx, meta, sharded=False)
         model2, _ = gu.build_model()
+        # the grid gradients start their all-reduce from a post-accumulate hook inside backward (big=1: every parameter)
+        hooks = parallel_mod().overlap_grid_allreduce(model2, big=1)
+        assert hooks
         out2, lo2, gcam2, g2, vox2 = _step(model2, fx, meta, sharded=True)
 
     def rel(a, b):
