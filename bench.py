@@ -459,17 +459,21 @@ def kernel_breakdown(step, dev):
     stream = torch.cuda.current_stream()
 
     def timed(fn0, n=5):
+        """median of n event-timed calls (a one-off allocator / lazy-init hiccup must not leak into a per-kernel figure)"""
         def fn():
             m.zero_grad(set_to_none=True)      # do not time gradient accumulation into 1 GB .grad buffers
             fn0()
         fn(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        ts = []
         for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
             fn()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
 
     res = {}
     coarse, fine, color = m.implicit_network.coarse, m.implicit_network.fine, m.rendering_network
