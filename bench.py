@@ -458,20 +458,22 @@ def kernel_breakdown(step, dev):
     view = torch.randn(P, 3, device=dev)
     stream = torch.cuda.current_stream()
 
-    def timed(fn0, n=5):
-        """median of n event-timed calls (a one-off allocator / lazy-init hiccup must not leak into a per-kernel figure)"""
+    def timed(fn0, n=5, reps=3):
+        """median over `reps` of (n back-to-back calls between two events) / n: launch latency is amortised over the queue,
+        and a one-off allocator / lazy-init hiccup cannot leak into a per-kernel figure"""
         def fn():
             m.zero_grad(set_to_none=True)      # do not time gradient accumulation into 1 GB .grad buffers
             fn0()
         fn(); torch.cuda.synchronize()
         ts = []
-        for _ in range(n):
+        for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            fn()
+            for _ in range(n):
+                fn()
             e1.record(stream)
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e1) / n)
         ts.sort()
         return ts[len(ts) // 2]
 
