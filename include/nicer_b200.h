@@ -158,6 +158,16 @@ int nicer_color_backward(const nicer_color_net_t *net, const float *x, const flo
 int nicer_outer_accum(const float *A, uint32_t lda, uint32_t M, const float *B, uint32_t ldb, uint32_t N,
                       uint32_t P, float *C, uint32_t ldc, float *bias, void *stream);
 
+/* Several contractions over the SAME P samples in one call (the weight gradients of one network backward): one kernel
+ * launch per 8 jobs instead of one per job.  `jobs` is a HOST array; each job has the meaning of nicer_outer_accum. */
+typedef struct {
+    const float *A; uint32_t lda, M;
+    const float *B; uint32_t ldb, N;
+    float *C; uint32_t ldc;
+    float *bias;
+} nicer_oa_job_t;
+int nicer_outer_accum_batch(const nicer_oa_job_t *jobs, uint32_t n_jobs, uint32_t P, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Density + alpha compositing, one warp per ray.  R rays x S samples (S <= 1024), P = R*S.
  *   sdf [P], x [P,3] (for the beta lookup), z [R,S], rgb [P,3], grad [P,3] (SDF gradients), voxels [res^3]

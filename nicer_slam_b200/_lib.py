@@ -22,6 +22,12 @@ class GridT(C.Structure):
                 ("divide_factor", C.c_float)]
 
 
+class OaJobT(C.Structure):
+    """nicer_oa_job_t (include/nicer_b200.h)."""
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_uint32), ("M", C.c_uint32), ("B", C.c_void_p), ("ldb", C.c_uint32),
+                ("N", C.c_uint32), ("C", C.c_void_p), ("ldc", C.c_uint32), ("bias", C.c_void_p)]
+
+
 class LossT(C.Structure):
     """nicer_loss_t (include/nicer_b200.h)."""
     _fields_ = ([(n, C.c_uint32) for n in ("R", "S", "B", "N", "G", "depth_mask_all")]
@@ -52,6 +58,7 @@ _SIGS = {
     "nicer_color_forward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32, _fp, _fp, _fp, _fp, _fp],
     "nicer_color_backward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32] + [_fp] * 14,
     "nicer_outer_accum": [_fp, _u32, _u32, _fp, _u32, _u32, _u32, _fp, _u32, _fp, _fp],
+    "nicer_outer_accum_batch": [C.POINTER(OaJobT), _u32, _u32, _fp],
     "nicer_composite_forward": [_fp] * 6 + [_u32, _u32, _u32] + [_fp] * 6,
     "nicer_composite_backward": [_fp] * 6 + [_u32, _u32, _u32] + [_fp] * 11,
     "nicer_sampler_weights": [_fp] * 4 + [_u32, _u32, _u32, _fp, _fp],

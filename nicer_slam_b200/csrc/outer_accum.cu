@@ -74,6 +74,8 @@ outer_accum_kernel(const float *__restrict__ A, uint32_t lda, uint32_t M, const 
 int launch_outer_accum_tc(const float *A, uint32_t lda, uint32_t M, const float *B, uint32_t ldb, uint32_t N, uint32_t P, float *C,
                           uint32_t ldc, float *bias, cudaStream_t st);
 
+int launch_outer_accum_batch_tc(const nicer_oa_job_t *jobs, uint32_t n_jobs, uint32_t P, uint8_t *done, cudaStream_t st);
+
 }  // namespace nicer
 
 using namespace nicer;
@@ -99,5 +101,25 @@ extern "C" int nicer_outer_accum(const float *A, uint32_t lda, uint32_t M, const
     else if (N <= 80) outer_accum_kernel<5><<<grid, OA_THREADS, 0, st>>>(A, lda, M, B, ldb, N, P, tpc, C, ldc, bias);
     else outer_accum_kernel<9><<<grid, OA_THREADS, 0, st>>>(A, lda, M, B, ldb, N, P, tpc, C, ldc, bias);
     NICER_CHECK_LAUNCH("nicer_outer_accum");
+    return 0;
+}
+
+extern "C" int nicer_outer_accum_batch(const nicer_oa_job_t *jobs, uint32_t n_jobs, uint32_t P, void *stream) {
+    if (n_jobs == 0 || P == 0) return 0;
+    if (!jobs) NICER_FAIL(-1, "nicer_outer_accum_batch: jobs is NULL");
+    if (n_jobs > 64) NICER_FAIL(-1, "nicer_outer_accum_batch: at most 64 jobs per call (got %u)", n_jobs);
+    for (uint32_t j = 0; j < n_jobs; ++j) {
+        const nicer_oa_job_t &q = jobs[j];
+        if (!q.A || !q.B || !q.C) NICER_FAIL(-1, "nicer_outer_accum_batch: NULL pointer in job %u", j);
+        if (q.M > 64 || q.N > 144) NICER_FAIL(-1, "nicer_outer_accum_batch: M <= 64 and N <= 144 required (job %u: %u, %u)", j, q.M, q.N);
+        if (q.lda < P || q.ldb < P || q.ldc < q.N) NICER_FAIL(-1, "nicer_outer_accum_batch: bad leading dimension in job %u", j);
+    }
+    uint8_t done[64] = {0};
+    if (int e = launch_outer_accum_batch_tc(jobs, n_jobs, P, done, (cudaStream_t)stream)) return e;
+    for (uint32_t j = 0; j < n_jobs; ++j) {
+        if (done[j] || jobs[j].M == 0 || jobs[j].N == 0) continue;
+        const nicer_oa_job_t &q = jobs[j];
+        if (int e = nicer_outer_accum(q.A, q.lda, q.M, q.B, q.ldb, q.N, P, q.C, q.ldc, q.bias, stream)) return e;
+    }
     return 0;
 }

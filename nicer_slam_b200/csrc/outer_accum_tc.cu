@@ -26,16 +26,28 @@ struct OtSmem {
     float acomb[OT_CH * 2 * OT_AROWS * 4];                        // 32 KB
 };
 
+// up to OT_MAX_JOBS contractions over the same sample range in one launch (the weight gradients of one network backward):
+// CTAs [j * ctas_per_job, (j+1) * ctas_per_job) split the stages of job j
+constexpr int OT_MAX_JOBS = 8;
+struct OtJobs {
+    const float *A[OT_MAX_JOBS], *B[OT_MAX_JOBS];
+    float *C[OT_MAX_JOBS], *bias[OT_MAX_JOBS];
+    uint32_t lda[OT_MAX_JOBS], ldb[OT_MAX_JOBS], ldc[OT_MAX_JOBS], M[OT_MAX_JOBS], N[OT_MAX_JOBS];
+};
+
 __global__ void __launch_bounds__(OT_THREADS, 2)
-outer_accum_tc_kernel(const float *__restrict__ A, uint32_t lda, uint32_t M, const float *__restrict__ B, uint32_t ldb, uint32_t N,
-                      uint32_t P, uint32_t stages_per_cta, float *C, uint32_t ldc, float *bias) {
+outer_accum_tc_kernel(const OtJobs js, uint32_t P, uint32_t stages_per_cta, uint32_t ctas_per_job) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     OtSmem &sm = *reinterpret_cast<OtSmem *>(smem_raw);
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t job = blockIdx.x / ctas_per_job, cta = blockIdx.x - job * ctas_per_job;
+    const float *__restrict__ A = js.A[job], *__restrict__ B = js.B[job];
+    float *C = js.C[job], *bias = js.bias[job];
+    const uint32_t lda = js.lda[job], ldb = js.ldb[job], ldc = js.ldc[job], M = js.M[job], N = js.N[job];
     const uint32_t n_stages = (P + OT_KC - 1) / OT_KC;
-    const uint32_t s0 = blockIdx.x * stages_per_cta;
+    const uint32_t s0 = cta * stages_per_cta;
     const uint32_t s1 = (s0 + stages_per_cta < n_stages) ? s0 + stages_per_cta : n_stages;
     const uint32_t n_units_b = ((N + 7) / 8) * 4;                 // units that touch real B rows
     const uint32_t n_units = OT_UNITS_A + n_units_b;
@@ -155,22 +167,58 @@ outer_accum_tc_kernel(const float *__restrict__ A, uint32_t lda, uint32_t M, con
 
 bool tc_enabled();
 
+static bool oa_tc_ok(const float *A, uint32_t lda, uint32_t M, const float *B, uint32_t ldb, uint32_t N, uint32_t P) {
+    if (M > OT_AROWS || N >= OT_BROWS || P < 4096) return false;
+    if ((lda & 3u) || (ldb & 3u) || (reinterpret_cast<uintptr_t>(A) & 15u) || (reinterpret_cast<uintptr_t>(B) & 15u)) return false;
+    return true;
+}
+
+static int oa_launch(const OtJobs &js, uint32_t n_jobs, uint32_t P, cudaStream_t st) {
+    const uint32_t n_stages = div_up(P, OT_KC);
+    uint32_t per_job = div_up((uint32_t)(2 * num_sms()), n_jobs);
+    if (per_job > n_stages) per_job = n_stages;
+    const uint32_t spc = div_up(n_stages, per_job);
+    per_job = div_up(n_stages, spc);
+    const size_t smem = sizeof(OtSmem);
+    NICER_CUDA(cudaFuncSetAttribute(outer_accum_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "nicer_outer_accum(tc)");
+    outer_accum_tc_kernel<<<per_job * n_jobs, OT_THREADS, smem, st>>>(js, P, spc, per_job);
+    NICER_CHECK_LAUNCH("nicer_outer_accum(tc)");
+    return 0;
+}
+
 // returns 1 when the tensor-core kernel was launched, 0 when the shapes do not qualify (caller falls back), < 0 on error
 int launch_outer_accum_tc(const float *A, uint32_t lda, uint32_t M, const float *B, uint32_t ldb, uint32_t N, uint32_t P, float *C,
                           uint32_t ldc, float *bias, cudaStream_t st) {
-    if (!tc_enabled()) return 0;
-    if (M > OT_AROWS || N >= OT_BROWS || P < 4096) return 0;
-    if ((lda & 3u) || (ldb & 3u) || (reinterpret_cast<uintptr_t>(A) & 15u) || (reinterpret_cast<uintptr_t>(B) & 15u)) return 0;
-    const uint32_t n_stages = div_up(P, OT_KC);
-    uint32_t grid = (uint32_t)(2 * num_sms());
-    if (grid > n_stages) grid = n_stages;
-    const uint32_t spc = div_up(n_stages, grid);
-    grid = div_up(n_stages, spc);
-    const size_t smem = sizeof(OtSmem);
-    NICER_CUDA(cudaFuncSetAttribute(outer_accum_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "nicer_outer_accum(tc)");
-    outer_accum_tc_kernel<<<grid, OT_THREADS, smem, st>>>(A, lda, M, B, ldb, N, P, spc, C, ldc, bias);
-    NICER_CHECK_LAUNCH("nicer_outer_accum(tc)");
+    if (!tc_enabled() || !oa_tc_ok(A, lda, M, B, ldb, N, P)) return 0;
+    OtJobs js{};
+    js.A[0] = A; js.B[0] = B; js.C[0] = C; js.bias[0] = bias;
+    js.lda[0] = lda; js.ldb[0] = ldb; js.ldc[0] = ldc; js.M[0] = M; js.N[0] = N;
+    if (int e = oa_launch(js, 1, P, st)) return e;
     return 1;
+}
+
+// all jobs of a batch in as few launches as possible; jobs the tensor-core kernel does not cover go one by one through
+// nicer_outer_accum's fallback
+int launch_outer_accum_batch_tc(const nicer_oa_job_t *jobs, uint32_t n_jobs, uint32_t P, uint8_t *done, cudaStream_t st) {
+    if (!tc_enabled()) return 0;
+    OtJobs js{};
+    uint32_t k = 0;
+    for (uint32_t j = 0; j < n_jobs; ++j) {
+        const nicer_oa_job_t &q = jobs[j];
+        done[j] = 0;
+        if (!oa_tc_ok(q.A, q.lda, q.M, q.B, q.ldb, q.N, P)) continue;
+        js.A[k] = q.A; js.B[k] = q.B; js.C[k] = q.C; js.bias[k] = q.bias;
+        js.lda[k] = q.lda; js.ldb[k] = q.ldb; js.ldc[k] = q.ldc; js.M[k] = q.M; js.N[k] = q.N;
+        done[j] = 1;
+        if (++k == OT_MAX_JOBS) {
+            if (int e = oa_launch(js, k, P, st)) return e;
+            k = 0;
+        }
+    }
+    if (k) {
+        if (int e = oa_launch(js, k, P, st)) return e;
+    }
+    return 0;
 }
 
 }  // namespace nicer

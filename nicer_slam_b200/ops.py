@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ColorNetT, GridT, LossT, SdfNetT
+from ._lib import ColorNetT, GridT, LossT, OaJobT, SdfNetT
 
 
 def lib():
@@ -182,6 +182,35 @@ def outer_accum(A, B, Cmat, bias=None, col0=0):
                                   ptr(bias) if bias is not None else None, stream()), "nicer_outer_accum")
 
 
+class OuterAccumBatch:
+    """Collects the weight / bias gradient contractions of one network backward (all over the same P samples) and issues
+    them through nicer_outer_accum_batch: one kernel launch per 8 jobs instead of one per job."""
+
+    def __init__(self):
+        self.jobs, self.keep = [], []
+
+    def add(self, A, B, Cmat, bias=None, col0=0):
+        if A.is_cuda and _WGRAD_LIBRARY_MIN_P == 0:        # NICER_WGRAD=cublas comparison path
+            outer_accum(A, B, Cmat, bias, col0)
+            return
+        j = OaJobT()
+        j.A, j.lda, j.M = _lib.require(A, torch.float32, "A").data_ptr(), A.stride(0), A.shape[0]
+        j.B, j.ldb, j.N = _lib.require(B, torch.float32, "B").data_ptr(), B.stride(0), B.shape[0]
+        j.C, j.ldc = _lib.require(Cmat, torch.float32, "C").data_ptr() + 4 * col0, Cmat.stride(0)
+        j.bias = _lib.require(bias, torch.float32, "bias").data_ptr() if bias is not None else None
+        self.jobs.append(j)
+        self.keep.append((A, B, Cmat, bias))
+        self.P = A.shape[1]
+
+    def flush(self):
+        if not self.jobs:
+            return
+        arr = (OaJobT * len(self.jobs))(*self.jobs)
+        check(lib().nicer_outer_accum_batch(arr, len(self.jobs), self.P, stream()), "nicer_outer_accum_batch")
+        _lib.launch_count += (len(self.jobs) + 7) // 8 - 1
+        self.jobs, self.keep = [], []
+
+
 # --------------------------------------------------------------------------------------------- SDF network
 class SdfNetFn(torch.autograd.Function):
     """(x, table, W0,b0,...,Wn,bn) -> (sdf [P,1], feat [P,F] (view of [F,P]), grad [P,3])."""
@@ -239,23 +268,25 @@ class SdfNetFn(torch.autograd.Function):
                                        ptr(grad_x), ptr(grad_table), ptr(ZB), ptr(QB), ptr(AB), ptr(TAN),
                                        ptr(T0), ptr(GY), stream(), _sptr(side)), "nicer_sdf_backward")
         grads = []
+        oa = OuterAccumBatch()
         for l in range(n + 1):
             W = wb[2 * l]
             dW, db = torch.zeros_like(W), torch.zeros(W.shape[0], device=dev)
             if l == 0:
-                outer_accum(ZB[:HIDDEN], H0, dW, db)
-                outer_accum(QB[:HIDDEN], T0, dW)
+                oa.add(ZB[:HIDDEN], H0, dW, db)
+                oa.add(QB[:HIDDEN], T0, dW)
             elif l < n:
-                outer_accum(ZB[l * HIDDEN:(l + 1) * HIDDEN], AB[(l - 1) * HIDDEN:l * HIDDEN], dW, db)
-                outer_accum(QB[l * HIDDEN:(l + 1) * HIDDEN], TAN[(l - 1) * HIDDEN:l * HIDDEN], dW)
+                oa.add(ZB[l * HIDDEN:(l + 1) * HIDDEN], AB[(l - 1) * HIDDEN:l * HIDDEN], dW, db)
+                oa.add(QB[l * HIDDEN:(l + 1) * HIDDEN], TAN[(l - 1) * HIDDEN:l * HIDDEN], dW)
             else:
                 a_n = AB[(n - 1) * HIDDEN:]
                 if gs is not None:
-                    outer_accum(gs.view(1, P), a_n, dW[:1], db[:1])
+                    oa.add(gs.view(1, P), a_n, dW[:1], db[:1])
                 if gf is not None and nfeat > 0:
-                    outer_accum(gf[:nfeat], a_n, dW[1:], db[1:])
+                    oa.add(gf[:nfeat], a_n, dW[1:], db[1:])
                 dW[0] += TAN[(n - 1) * HIDDEN:].sum(dim=1)
             grads += [dW, db]
+        oa.flush()
         _join(side, None, defer=False)       # the scatter overlapped with the weight-gradient GEMMs above
         return (grad_x, grad_table, None, None, None, *grads)
 
@@ -327,6 +358,7 @@ class ColorNetFn(torch.autograd.Function):
                                          ptr(grad_normals), ptr(grad_feat_fm), ptr(grad_table), ptr(ZB), ptr(OB),
                                          ptr(GY), stream(), _sptr(side)), "nicer_color_backward")
         grads = []
+        oa = OuterAccumBatch()
         for l in range(n + 1):
             W = wb[2 * l]
             dW, db = torch.zeros_like(W), torch.zeros(W.shape[0], device=dev)
@@ -334,15 +366,16 @@ class ColorNetFn(torch.autograd.Function):
                 # input = [x, PE(view), normals (33) | feat (F) | grid]: the feature block reads feat_fm in place, the
                 # forward kernel only materialised the 33 + L*C other rows of H0
                 nf = meta.feature
-                outer_accum(ZB[:HIDDEN], H0[:33], dW, db)
-                outer_accum(ZB[:HIDDEN], feat_fm, dW, None, col0=33)
+                oa.add(ZB[:HIDDEN], H0[:33], dW, db)
+                oa.add(ZB[:HIDDEN], feat_fm, dW, None, col0=33)
                 if meta.d_in > 33 + nf:
-                    outer_accum(ZB[:HIDDEN], H0[33 + nf:], dW, None, col0=33 + nf)
+                    oa.add(ZB[:HIDDEN], H0[33 + nf:], dW, None, col0=33 + nf)
             elif l < n:
-                outer_accum(ZB[l * HIDDEN:(l + 1) * HIDDEN], A_fm[(l - 1) * HIDDEN:l * HIDDEN], dW, db)
+                oa.add(ZB[l * HIDDEN:(l + 1) * HIDDEN], A_fm[(l - 1) * HIDDEN:l * HIDDEN], dW, db)
             else:
-                outer_accum(OB, A_fm[(n - 1) * HIDDEN:], dW, db)
+                oa.add(OB, A_fm[(n - 1) * HIDDEN:], dW, db)
             grads += [dW, db]
+        oa.flush()
         # the color grid is used once per forward: its gradient is only read after the backward pass, so the scatter may
         # keep running under the SDF backward kernels -- unless AccumulateGrad is about to add to an existing .grad
         leaf = ctx.table_leaf

@@ -148,6 +148,15 @@ extern "C" int nicer_outer_accum(const float *A, uint32_t lda, uint32_t M, const
     return 0;
 }
 
+extern "C" int nicer_outer_accum_batch(const nicer_oa_job_t *jobs, uint32_t n_jobs, uint32_t P, void *st) {
+    for (uint32_t j = 0; j < n_jobs; ++j) {
+        const nicer_oa_job_t &q = jobs[j];
+        if (q.M == 0 || q.N == 0) continue;
+        nicer_outer_accum(q.A, q.lda, q.M, q.B, q.ldb, q.N, P, q.C, q.ldc, q.bias, st);
+    }
+    return 0;
+}
+
 static void ray_forward(const float *sdf, const float *X, const float *Z, const float *voxels, int res, uint32_t r,
                         uint32_t S, std::vector<float> &E, std::vector<float> &T, std::vector<float> &beta) {
     float carry = 0.f;
