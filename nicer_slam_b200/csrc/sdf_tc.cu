@@ -1,7 +1,9 @@
 // Tensor-core (tcgen05, sm_100a) SDF-only forward: the sampler's 640-samples-per-ray pass and get_sdf_vals
 // (/root/reference/code/model/ray_sampler.py:100-102, model/base_networks.py:27-32,223-228).
 //
-// One CTA = 128 threads = 128 points = the 128 TMEM lanes of one accumulator tile.  Per point, one thread builds the
+// Two kernels: sdf_only_tc4_kernel (default: four 128-point tiles per SM, K fed in 32-column chunks, grid features read from
+// a scratch filled by grid_encode_kernel) and the earlier sdf_only_tc_kernel (NICER_TC_TILES=2: two tiles per SM, whole-K
+// operands, gathers inline), kept for comparison.  In both, one thread = one point = one TMEM lane: the thread builds the
 // network input (x, NeRF PE, hash/dense grid features) in registers and writes it with tcgen05.st into TMEM as the
 // A operand (hi and lo halves of the 3xTF32 split); thread 0 issues tcgen05.mma kind::tf32 (M=128, N=64, K=8 per
 // instruction; 3 MMAs per K-step for fp32 fidelity) against the weights held in shared memory in the UMMA K-major

@@ -1,7 +1,8 @@
 """SLAMLoss with the reference's constructor / call contract and output keys
 (/root/reference/code/model/loss.py:8-233): weighted sum of RGB L1, photometric warp L1, eikonal, smoothness,
 scale-and-shift-invariant mono depth, mono normal (L1 + cosine), sensor depth and optical-flow terms.
-All terms are reductions over O(rays) tensors; they run as plain device-side PyTorch (no host sync).
+The ray / eikonal-point terms and their gradients run in the fused kernels of csrc/loss.cu (ops.SlamLossFn); the warp and
+flow terms are masked L1 means in PyTorch.  No host sync anywhere.
 
 Drop-in: ``train.loss_class = "nicer_slam_b200.model.loss.SLAMLoss"``.
 """

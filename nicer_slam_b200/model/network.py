@@ -2,9 +2,9 @@
 (/root/reference/code/model/network.py:14-370), running the per-iteration volume-rendering step on the
 fused sm_100a kernels:
 
-    rays (torch, differentiable w.r.t. pose) -> sampler (fused sdf-only + density/transmittance kernels)
-    -> SDF nets (one fused kernel per net: gather + PE + MLP + d sdf/dx) -> color net (fused)
-    -> density + compositing (warp-scan kernel) -> depth / normal maps, flow, warp, eikonal samples.
+    rays / points (camera kernels, differentiable w.r.t. pose) -> sampler (gather kernel + tcgen05 sdf-only MLP kernel per net,
+    density/transmittance kernel) -> SDF nets (gather kernel -> tcgen05 MLP + d sdf/dx kernels) -> color net (same split)
+    -> density + compositing (warp-scan kernel) -> depth / normal maps, flow, warp sampling kernel, eikonal samples.
 
 Drop-in: ``train.model_class = "nicer_slam_b200.model.network.SLAMNetwork"`` in the conf.
 Multi-GPU (ray-parallel): see nicer_slam_b200/parallel.py.
