@@ -334,16 +334,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from nicer_slam_b200 import parallel
 
-    step = build_step(args.rays, args.frames, args.color_logmap, dev, seed=rank)
-    if world > 1 and os.environ.get("NICER_OVERLAP_ALLREDUCE", "1") == "1":
-        parallel.overlap_grid_allreduce(step.model)     # the 1 GB color-grid all-reduce runs under the SDF backward
-    P = args.rays * S_MAIN
+    # Weak scaling: the global batch is `world` x args.rays rays (every frame contributes world x rays/frames pixels); every
+    # rank holds the SAME weights and the SAME full-batch inputs (seed independent of the rank), SLAMNetwork.forward takes the
+    # rank's pixel share, gathers the per-ray outputs (one packed all-gather), every rank evaluates the loss on the full batch
+    # and the gradient reducer sums grids / MLP weights / poses inside backward (nicer_slam_b200/parallel.py).
+    step = build_step(args.rays * world, args.frames, args.color_logmap, dev, seed=0)
+    P = args.rays * S_MAIN                                     # ray-samples per GPU per step
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)   # 192 MiB > 126 MB L2
 
     graphed = None
-    if not args.no_graph and world == 1:    # N > 1 runs eagerly: the step contains NCCL collectives (voxel counter)
+    if not args.no_graph and (world == 1 or os.environ.get("NICER_BENCH_GRAPH_MULTI", "1") == "1"):
         from nicer_slam_b200.graph import GraphedStep
-        graphed = GraphedStep(lambda: step.run(), warmup=3)     # forward + loss + backward as ONE CUDA graph
+        # forward + loss + backward (for N > 1 including the NCCL all-gather / all-reduces) as ONE CUDA graph
+        graphed = GraphedStep(lambda: step.run(), warmup=3)
 
     def one(e2e=False):
         flush.add_(1.0)                                         # L2 flush between timed iterations
@@ -355,8 +358,6 @@ def main():
             v = float(loss.item()) if e2e else loss
         else:
             v = step.run_e2e() if e2e else step.run()
-        if world > 1:
-            parallel.allreduce_gradients(step.model, extra=[step.cam7])
         return v
 
     # launches of our kernels per step (counted on an eager step; a graph replay launches the same kernels)
@@ -423,12 +424,20 @@ def main():
         v, dt, threads = time_cpu(2048, 16, 1, 1)
         cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
                "sample": "2048 of the 4096 rays of one step (16 frames x 128 px), color grid 2^19/level, 1 timed step after a 16-ray warm-up"}
+    comm = None
+    if world > 1:
+        red = parallel.reducer_for(step.model)
+        comm = {"allreduce_grid_bytes": red.bytes_big, "allreduce_small_bytes": red.bytes_small,
+                "note": "per step and rank: in-place NCCL all-reduce of the grid gradients (started from post-accumulate hooks, "
+                        "the 1 GB color grid under the SDF backward), one flat all-reduce of the MLP gradients, one packed "
+                        "all-gather of the per-ray outputs, a 1 MB voxel-counter all-reduce, a 16x4x4 pose-gradient all-reduce"}
     if rank == 0:
         peaks = _peaks()
         line = {"metric": "ray-samples/sec fwd+bwd", "value": value, "unit": "ray-samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "rays_per_gpu": args.rays, "ray_samples_per_step_per_gpu": P,
+                           "global_rays": args.rays * world,
                            "color_grid_log2_entries": args.color_logmap, "parallelism": f"ray-parallel x{world}",
                            "l2": "192 MiB flush buffer written between timed iterations; color grid (1 GB) > L2"},
                 "clocks": clk.summary(), "gpu_launches": launches if graphed is None else launches_per_step * args.steps,
@@ -437,12 +446,16 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "ray-samples/s", "h2d_bytes_per_step": step.h2d_bytes(), "d2h_bytes_per_step": 4,
                         "note": "frames (full_rgb/full_depth) are a device-resident cache; per-step uv/pose/K/sampled GT come from pinned host memory"}}
         line.update(extra)
+        if comm:
+            line["comm"] = comm
         if "roofline" in line:
             line["roofline"]["peak_source"] = peaks["source"]
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -59,7 +59,10 @@ class SLAMNetwork(nn.Module):
         self.register_buffer("voxels", torch.zeros(self.voxel_res, self.voxel_res, self.voxel_res), persistent=False)
         self.voxels_shape = self.voxels.shape
         self.rng = DeviceRng()
-        self.ray_parallel = True   # under torch.distributed: rays are sharded over ranks (parallel.py)
+        # under torch.distributed (parallel.py): True = forward shards the rays itself and returns full-batch outputs;
+        # "explicit" = the caller shards (parallel.shard_batch / gather_outputs), only the voxel counter is synchronised here;
+        # False = every rank is an independent replica
+        self.ray_parallel = True
         self._sync_density_voxels()
 
     def _sync_density_voxels(self):
@@ -92,6 +95,15 @@ class SLAMNetwork(nn.Module):
         self._sync_density_voxels()
 
         intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
+        # ray-parallel: under torch.distributed every rank renders its contiguous share of the pixels of every
+        # frame; the output dictionary is gathered back to the full batch below and the gradient reducer is armed for the
+        # backward pass that follows, so the trainer's forward / loss / backward / step sequence runs unchanged
+        sharded = self.ray_parallel is True and parallel.world() > 1 and ("vis" not in mode)
+        if sharded:
+            uv = uv[:, parallel.pixel_slice(uv.shape[1])].contiguous()
+            pose = parallel.sum_grad_over_ranks(pose)
+            if torch.is_grad_enabled():
+                parallel.reducer_for(self).arm()
         ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
         eye = torch.eye(4, device=pose.device, dtype=pose.dtype)[None].repeat(pose.shape[0], 1, 1)
         depth_scale = rend_util.get_camera_params(uv, eye, intrinsics)[0][:, :, 2:]   # unnormalised z (F5)
@@ -168,6 +180,8 @@ class SLAMNetwork(nn.Module):
 
         normal_map = normal_map.reshape(bs, -1, 3)
         output["normal_map"] = torch.einsum("bij,bni->bnj", pose[:, :3, :3], normal_map)
+        if sharded:
+            output = parallel.gather_outputs(output, bs)
         return output
 
     # ------------------------------------------------------------------------------------------------

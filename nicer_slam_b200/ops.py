@@ -153,6 +153,10 @@ def _fm(t):
 
 
 def _c(t):
+    """Contiguous version of t (None stays None).  The result must be bound to a name that outlives the library call:
+    a temporary passed as ``ptr(_c(t))`` would be freed before the (host-emulated) kernel reads it."""
+    if t is None:
+        return None
     return t if t.is_contiguous() else t.contiguous()
 
 
@@ -415,11 +419,11 @@ class CompositeFn(torch.autograd.Function):
         g_sdf = torch.empty(R * S, device=dev)
         g_rgb = torch.empty(R * S, 3, device=dev)
         g_grad = torch.empty(R * S, 3, device=dev)
-        opt = lambda t: ptr(_c(t)) if t is not None else None  # noqa: E731
         gd = _c(g_depth.reshape(R)) if g_depth is not None else None
+        g_rgb_out, g_normal, g_w = _c(g_rgb_out), _c(g_normal), _c(g_w)
         check(lib().nicer_composite_backward(ptr(sdf_), ptr(x_), ptr(z_), ptr(rgb_), ptr(grad_), ptr(vox),
-                                             vox.shape[0], R, S, ptr(weights), ptr(depth), ptr(wsum), opt(g_rgb_out),
-                                             ptr(gd), opt(g_normal), opt(g_w), ptr(g_sdf), ptr(g_rgb), ptr(g_grad),
+                                             vox.shape[0], R, S, ptr(weights), ptr(depth), ptr(wsum), ptr(g_rgb_out),
+                                             ptr(gd), ptr(g_normal), ptr(g_w), ptr(g_sdf), ptr(g_rgb), ptr(g_grad),
                                              stream()), "nicer_composite_backward")
         return g_sdf.view(ctx.sdf_shape), None, None, g_rgb, g_grad, None
 
@@ -427,8 +431,8 @@ class CompositeFn(torch.autograd.Function):
 def sampler_weights(sdf, x, z, voxels):
     R, S = z.shape
     w = torch.empty(R, S, device=z.device)
-    vox = _c(voxels)
-    check(lib().nicer_sampler_weights(ptr(_c(sdf.reshape(-1))), ptr(_c(x)), ptr(_c(z)), ptr(vox), vox.shape[0], R, S,
+    vox, sdf, x, z = _c(voxels), _c(sdf.reshape(-1)), _c(x), _c(z)
+    check(lib().nicer_sampler_weights(ptr(sdf), ptr(x), ptr(z), ptr(vox), vox.shape[0], R, S,
                                       ptr(w), stream()), "nicer_sampler_weights")
     return w
 
@@ -490,9 +494,10 @@ class _HashEncodeBackward(torch.autograd.Function):
             raise RuntimeError("hash_encode: second backward requires calc_grad_inputs (dy_dx was not computed)")
         grad_grad = torch.zeros_like(grad)
         grad2_embeddings = torch.zeros_like(embeddings)
+        ggi = _c(ggi)
         check(lib().nicer_hash_encode_second_backward(ptr(grad), ptr(inputs), ptr(embeddings),
                                                       ptr(offsets, torch.int32), B, D, Cc, L, S, H, int(cgi), ptr(dy_dx),
-                                                      ptr(_c(ggi)), ptr(grad_grad), ptr(grad2_embeddings), stream()),
+                                                      ptr(ggi), ptr(grad_grad), ptr(grad2_embeddings), stream()),
               "nicer_hash_encode_second_backward")
         return grad_grad, None, grad2_embeddings, None, None, None
 
@@ -517,7 +522,8 @@ class PoseFromCam7Fn(torch.autograd.Function):
     def backward(ctx, g_pose):
         (cam7,) = ctx.saved_tensors
         g = torch.empty_like(cam7)
-        check(lib().nicer_pose_from_cam7_backward(ptr(cam7), ptr(_c(g_pose)), cam7.shape[0], ptr(g), stream()),
+        g_pose = _c(g_pose)
+        check(lib().nicer_pose_from_cam7_backward(ptr(cam7), ptr(g_pose), cam7.shape[0], ptr(g), stream()),
               "nicer_pose_from_cam7_backward")
         return g
 
@@ -544,8 +550,8 @@ class CameraRaysFn(torch.autograd.Function):
         if g_dirs is None:
             g_dirs = torch.zeros(B, N, 3, device=uv.device)
         g_pose = torch.empty(B, 4, 4, device=uv.device)
-        check(lib().nicer_camera_rays_backward(ptr(uv), ptr(pose), ptr(K), B, N, ptr(_c(g_dirs)),
-                                               ptr(_c(g_loc)) if g_loc is not None else None, ptr(g_pose), stream()),
+        g_dirs, g_loc = _c(g_dirs), _c(g_loc)
+        check(lib().nicer_camera_rays_backward(ptr(uv), ptr(pose), ptr(K), B, N, ptr(g_dirs), ptr(g_loc), ptr(g_pose), stream()),
               "nicer_camera_rays_backward")
         return None, g_pose, None
 
@@ -571,8 +577,8 @@ class RayPointsFn(torch.autograd.Function):
         R, S = z.shape
         g_loc = torch.empty(R, 3, device=z.device)
         g_dirs = torch.empty(R, 3, device=z.device)
-        check(lib().nicer_ray_points_backward(ptr(z), R, S, ptr(_c(g_points)) if g_points is not None else None,
-                                              ptr(_c(g_dirs_flat)) if g_dirs_flat is not None else None, ptr(g_loc),
+        g_points, g_dirs_flat = _c(g_points), _c(g_dirs_flat)
+        check(lib().nicer_ray_points_backward(ptr(z), R, S, ptr(g_points), ptr(g_dirs_flat), ptr(g_loc),
                                               ptr(g_dirs), stream()), "nicer_ray_points_backward")
         return g_loc, g_dirs, None
 
@@ -669,7 +675,8 @@ class WarpSampleFn(torch.autograd.Function):
         g_dirs = torch.empty_like(dirs_p)
         g_loc = torch.zeros(B, 3, device=dev)
         g_w2c = torch.zeros(B, 4, 4, device=dev)
+        g_sampled = _c(g_sampled)
         check(lib().nicer_warp_sample_backward(ptr(depth), ptr(dirs_p), ptr(loc_p), ptr(w2c), ptr(K), ptr(img), B, N, pp, H, W,
-                                               ptr(_c(g_sampled)), ptr(g_depth), ptr(g_dirs), ptr(g_loc), ptr(g_w2c), stream()),
+                                               ptr(g_sampled), ptr(g_depth), ptr(g_dirs), ptr(g_loc), ptr(g_w2c), stream()),
               "nicer_warp_sample_backward")
         return g_depth, g_dirs, g_loc, g_w2c, None, None, None
