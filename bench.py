@@ -456,6 +456,12 @@ def main():
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
+        if graphed is not None:
+            # every rank is done (barrier above).  A communicator whose kernels sit in a live CUDA graph does not tear down
+            # (measured: destroy_process_group() never returns), so leave without the NCCL teardown
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
     return 0
 

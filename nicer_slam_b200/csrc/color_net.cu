@@ -51,7 +51,7 @@ __device__ void stage_color_net(const nicer_color_net_t &net, const LevelScales 
     for (int i = tid; i < 3 * NICER_W; i += nt) smem[lay.WL + i] = net.W[n][i];
     for (int i = tid; i < NICER_W; i += nt) smem[lay.b0 + i] = net.b[0][i];
     LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
-    for (int l = tid; l < L; l += nt) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    for (int l = tid; l < L; l += nt) lv[l] = make_level(net.grid.offsets, (uint32_t)l, level_scale(ls, (uint32_t)l));
     nv.W0t = W0t;
     for (int i = 0; i < 3; ++i) { nv.Wt[i] = smem + lay.Wt[i]; nv.b[i] = smem + lay.b[i]; }
     nv.WL = smem + lay.WL;

@@ -100,7 +100,7 @@ color_forward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, const
     for (int i = tid; i < NICER_W; i += TCF_THREADS) { smem[pl.b0 + i] = net.b[0][i]; smem[pl.b1 + i] = net.b[1][i]; }
     for (int i = tid; i < 3 * NICER_W; i += TCF_THREADS) smem[pl.wl + i] = net.W[2][i];
     LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + pl.lv);
-    for (int l = tid; l < L; l += TCF_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    for (int l = tid; l < L; l += TCF_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, level_scale(ls, (uint32_t)l));
     Tile t = tile_setup(sh, CT_ALO, CT_D);
     const size_t Ps = P;
     const float df = has_grid ? net.grid.divide_factor : 1.0f;
@@ -227,7 +227,7 @@ color_backward_tc_kernel(const nicer_color_net_t net, const LevelScales ls, cons
     ct_stage(NICER_W, NICER_W, smem + pl.w_hi[2], smem + pl.w_lo[2], [&](int n, int k) { return W0[(size_t)k * d_in + 33 + n]; });
     for (int i = tid; i < 3 * NICER_W; i += TCF_THREADS) smem[pl.wl + i] = net.W[2][i];
     LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + pl.lv);
-    for (int l = tid; l < L; l += TCF_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    for (int l = tid; l < L; l += TCF_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, level_scale(ls, (uint32_t)l));
     Tile t = tile_setup(sh, CB_ALO, CB_D);
     const size_t Ps = P;
     const float df = has_grid ? net.grid.divide_factor : 1.0f;

@@ -24,7 +24,7 @@ grid_encode_kernel(const nicer_grid_t g, const LevelScales ls, const float *__re
     const float x[3] = {__ldg(X + 3 * (size_t)p), __ldg(X + 3 * (size_t)p + 1), __ldg(X + 3 * (size_t)p + 2)};
     float u[3];
     to_unit(x, g.divide_factor, u);
-    const LevelInfo li = make_level(g.offsets, l, ls.s[l]);
+    const LevelInfo li = make_level(g.offsets, l, level_scale(ls, (uint32_t)l));
     float feat[C], dfeat[3][C];
     encode_level<C, WITH_DX>(g.table, li, u, feat, dfeat);
 #pragma unroll

@@ -57,7 +57,7 @@ grid_scatter_kernel(const nicer_grid_t g, const LevelScales ls, const float *__r
     const uint32_t p0 = run * GS_RUN;
     if (p0 >= P) return;
     const size_t Ps = P;
-    const LevelInfo li = make_level(g.offsets, l, ls.s[l]);
+    const LevelInfo li = make_level(g.offsets, l, level_scale(ls, (uint32_t)l));
     float acc[8][C];
     Cell3 cur;
     bool have = false;

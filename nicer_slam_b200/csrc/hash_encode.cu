@@ -101,7 +101,7 @@ hash_forward_kernel(const float *__restrict__ inputs, const float *__restrict__ 
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
-    const LevelInfo li = make_level(offsets, level, ls.s[level]);
+    const LevelInfo li = make_level(offsets, level, level_scale(ls, (uint32_t)level));
     const float *tab = grid + (size_t)li.offset * C;
     const Cell<D> c = locate<D>(li, inputs + (size_t)b * D);
     float *out = outputs + ((size_t)level * B + b) * C;
@@ -163,7 +163,7 @@ hash_backward_kernel(const float *__restrict__ grad, const float *__restrict__ i
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t level = blockIdx.y;
-    const LevelInfo li = make_level(offsets, level, ls.s[level]);
+    const LevelInfo li = make_level(offsets, level, level_scale(ls, (uint32_t)level));
     const Cell<D> c = locate<D>(li, inputs + (size_t)b * D);
     if (!c.inside) return;
     float g[C];
@@ -238,7 +238,7 @@ hash_second_backward_kernel(const float *__restrict__ grad, const float *__restr
         }
         vec_store<C>(grad_grad + ((size_t)level * B + b) * C, r);
     }
-    const LevelInfo li = make_level(offsets, level, ls.s[level]);
+    const LevelInfo li = make_level(offsets, level, level_scale(ls, (uint32_t)level));
     const Cell<D> c = locate<D>(li, inputs + (size_t)b * D);
     if (!c.inside) return;
     float g[C];

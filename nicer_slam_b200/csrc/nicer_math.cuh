@@ -149,16 +149,28 @@ struct LevelInfo {
 constexpr uint32_t LEVEL_MOD_GENERAL = 0u, LEVEL_MOD_MASK = 1u, LEVEL_MOD_WRAP = 2u;
 constexpr int LEVEL_INFO_WORDS = sizeof(LevelInfo) / 4;
 
-// Per-level scales exp2f(level*S)*H - 1 are evaluated on the HOST (common.cuh: host_level_scales) in the same fp32
-// steps as the reference (hashencoder.cu:180) and handed to the kernels by value: CUDA's exp2f (2 ulp) and glibc's
-// (correctly rounded) differ in the last bit for non-integer exponents, and one ulp of `scale` at resolution 2048
-// already moves a sample by 1e-4 of a cell.
-struct LevelScales { float s[16]; };
+// Per-level scale exp2f(level*S)*H - 1 (hashencoder.cu:180).  The kernels evaluate it on the DEVICE with the reference's own
+// expression, so that nvcc emits what it emits for the reference (MUFU.EX2 + one FFMA: see the SASS of kernel_grid in
+// oracle/_ref) and sample positions are bit-identical to the reference's CUDA build on the same GPU: one ulp of `scale` at
+// resolution 2048 already moves a sample by 1e-4 of a cell (tests/test_gpu_ref_cuda.py).  The host-compiled emulation of
+// the per-point functions (tests/host_emul, CPU tests only) and the CPU oracle use the C library's exp2f; against those the
+// GPU differs by that last bit of scale (~1e-5 relative on interpolated features at the finest levels).
+struct LevelScales { float s[16]; float S; uint32_t H; };
 
 inline LevelScales host_level_scales(uint32_t L, float S, uint32_t H) {
     LevelScales ls;
     for (uint32_t l = 0; l < 16; ++l) ls.s[l] = (l < L) ? exp2f((float)l * S) * (float)H - 1.0f : 0.f;
+    ls.S = S;
+    ls.H = H;
     return ls;
+}
+
+NHD float level_scale(const LevelScales &ls, uint32_t level) {
+#ifdef __CUDA_ARCH__
+    return exp2f(level * ls.S) * ls.H - 1.0f;
+#else
+    return ls.s[level];
+#endif
 }
 
 NHD bool level_is_dense(const LevelInfo &li);

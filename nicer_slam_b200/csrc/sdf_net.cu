@@ -69,7 +69,7 @@ __device__ void stage_sdf_net(const nicer_sdf_net_t &net, const LevelScales &ls,
         }
     }
     LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
-    for (int l = tid; l < L; l += nt) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    for (int l = tid; l < L; l += nt) lv[l] = make_level(net.grid.offsets, (uint32_t)l, level_scale(ls, (uint32_t)l));
     nv.W0t = W0t;
     for (int i = 0; i < 3; ++i) { nv.Wt[i] = smem + lay.Wt[i]; nv.b[i] = smem + lay.b[i]; }
     nv.WLt = smem + lay.WLt;

@@ -76,7 +76,7 @@ sdf_only_tc_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcSmem
     }
     for (int i = tid; i < NICER_W; i += TC_BLOCK) smem[lay.wl_sdf + i] = net.W[n][i];
     LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
-    for (int l = tid; l < L; l += TC_BLOCK) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    for (int l = tid; l < L; l += TC_BLOCK) lv[l] = make_level(net.grid.offsets, (uint32_t)l, level_scale(ls, (uint32_t)l));
     if (tid == 0) { tc::mbar_init(&mma_bar, 1); tc::fence_mbar_init(); }
     if (warp == 0) tc::tmem_alloc(&tmem_base_slot, TC_TMEM_COLS);
     // make the generic-proxy weight writes visible to the tensor core (async proxy) before any MMA
@@ -257,7 +257,7 @@ sdf_only_tc4_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcSme
     }
     for (int i = tid; i < NICER_W; i += T4_THREADS) smem[lay.wl_sdf + i] = net.W[n][i];
     LevelInfo *lv = reinterpret_cast<LevelInfo *>(smem + lay.lv);
-    for (int l = tid; l < L; l += T4_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    for (int l = tid; l < L; l += T4_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, level_scale(ls, (uint32_t)l));
     if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
     if (warp == 0) tc::tmem_alloc(&tmem_base_slot, T4_CTA_COLS);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

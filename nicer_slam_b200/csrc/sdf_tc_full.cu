@@ -157,7 +157,7 @@ __device__ __forceinline__ Tile tcf_setup(const nicer_sdf_net_t &net, const Leve
     }
     for (int i = tid; i < NICER_W; i += TCF_THREADS) smem[pl.wl_sdf + i] = net.W[n][i];
     lv = reinterpret_cast<LevelInfo *>(smem + pl.lv);
-    for (int l = tid; l < L; l += TCF_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, ls.s[l]);
+    for (int l = tid; l < L; l += TCF_THREADS) lv[l] = make_level(net.grid.offsets, (uint32_t)l, level_scale(ls, (uint32_t)l));
     return tile_setup(sh, TCF_ALO, TCF_D);
 }
 
