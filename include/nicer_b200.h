@@ -191,6 +191,40 @@ int nicer_composite_backward(const float *sdf, const float *x, const float *z, c
 int nicer_sampler_weights(const float *sdf, const float *x, const float *z, const float *voxels,
                           uint32_t voxel_res, uint32_t R, uint32_t S, float *weights, void *stream);
 
+/* ---- weight_norm of all Linear layers of a network in one launch (torch._weight_norm, dim 0; model/base_networks.py:149-153):
+ * forward: w[r,:] = g[r] * v[r,:] / ||v[r,:]||, norm[r] = ||v[r,:]|| (norm optional); backward (needs norm): dv, dg from dw. */
+#define NICER_WN_MAX_JOBS 8
+typedef struct {
+    const float *v;      /* [rows, cols] */
+    const float *g;      /* [rows] */
+    float *w;            /* forward out [rows, cols] */
+    float *norm;         /* forward out / backward in [rows] */
+    const float *dw;     /* backward in [rows, cols] */
+    float *dv;           /* backward out [rows, cols] */
+    float *dg;           /* backward out [rows] */
+    uint32_t rows, cols;
+} nicer_wn_job_t;
+int nicer_weight_norm(const nicer_wn_job_t *jobs, uint32_t n, void *stream);
+int nicer_weight_norm_backward(const nicer_wn_job_t *jobs, uint32_t n, void *stream);
+
+/* Coarse depths of the hierarchical sampler (UniformSampler.get_z_vals + near_far_from_cube, model/ray_sampler.py:21-61):
+ * far[r] = exit of ray r from the cube [-bound, bound]^3 clamped to far_cap (use_cube = take_sphere_intersection; else
+ * far_cap itself), z[r, i] = near*(1-t_i) + far*t_i with t = linspace(0, 1, N), stratified inside the half-way intervals
+ * with the caller's uniform draws rnd [R,N] (NULL: no jitter, model.eval()); points [R*N,3] = cam_loc + z*ray_dir
+ * (optional).  cam_loc, ray_dirs [R,3]. */
+int nicer_sampler_uniform(const float *cam_loc, const float *ray_dirs, float near, float far_cap, float bound, int use_cube,
+                          const float *rnd, uint32_t R, uint32_t N, float *z, float *far, float *points, void *stream);
+
+/* The rest of ImportantSampler.get_z_vals (model/ray_sampler.py:105-159), one warp per ray: weights of the U coarse
+ * samples from their SDF (density, transmittance), pdf = (w[:-1]+1e-5)/sum, cdf, inverse CDF at linspace(0,1,N)
+ * (searchsorted right=True, the reference's denom < 1e-5 rule), merged with near, far[r] and the n_extra coarse depths
+ * z[r, sel[j]], sorted -> z_out [R, N+2+n_extra]; z_eik[r] = z_out[r, eik_idx[r]] (optional).  weights [R,U] optional
+ * output.  sel, eik_idx: int64 (torch.randperm / torch.randint results).  U <= 1024, N+2+n_extra <= 256. */
+int nicer_sampler_resample(const float *sdf, const float *x, const float *z, const float *voxels, uint32_t voxel_res,
+                           uint32_t R, uint32_t U, uint32_t N, const int64_t *sel, uint32_t n_extra, float near,
+                           const float *far, const int64_t *eik_idx, float *z_out, float *z_eik, float *weights,
+                           void *stream);
+
 /* voxels[idx(x)] += 1 for every point with all |x_i| <= 0.99 (network.py:62-76). */
 int nicer_voxel_count(const float *x, uint32_t P, float *voxels, uint32_t voxel_res, void *stream);
 

@@ -28,6 +28,11 @@ class OaJobT(C.Structure):
                 ("N", C.c_uint32), ("C", C.c_void_p), ("ldc", C.c_uint32), ("bias", C.c_void_p)]
 
 
+class WnJobT(C.Structure):
+    """nicer_wn_job_t (include/nicer_b200.h)."""
+    _fields_ = [(n, C.c_void_p) for n in ("v", "g", "w", "norm", "dw", "dv", "dg")] + [("rows", C.c_uint32), ("cols", C.c_uint32)]
+
+
 class LossT(C.Structure):
     """nicer_loss_t (include/nicer_b200.h)."""
     _fields_ = ([(n, C.c_uint32) for n in ("R", "S", "B", "N", "G", "depth_mask_all")]
@@ -63,6 +68,10 @@ _SIGS = {
     "nicer_composite_backward": [_fp] * 6 + [_u32, _u32, _u32] + [_fp] * 11,
     "nicer_sampler_weights": [_fp] * 4 + [_u32, _u32, _u32, _fp, _fp],
     "nicer_voxel_count": [_fp, _u32, _fp, _u32, _fp],
+    "nicer_weight_norm": [C.POINTER(WnJobT), _u32, _fp],
+    "nicer_weight_norm_backward": [C.POINTER(WnJobT), _u32, _fp],
+    "nicer_sampler_uniform": [_fp, _fp, C.c_float, C.c_float, C.c_float, C.c_int, _fp, _u32, _u32, _fp, _fp, _fp, _fp],
+    "nicer_sampler_resample": [_fp, _fp, _fp, _fp, _u32, _u32, _u32, _u32, _fp, _u32, C.c_float, _fp, _fp, _fp, _fp, _fp, _fp],
     "nicer_set_tensor_cores": [C.c_int],
     "nicer_slam_loss": [C.POINTER(LossT), _fp, _fp, _fp, _fp],
     "nicer_warp_sample": [_fp] * 6 + [_u32] * 5 + [_fp, _fp, _fp],

@@ -17,12 +17,43 @@ from ..hashencoder.hashgrid import HashEncoder
 from .embedder import get_embedder
 
 
+# Effective (weight-normed) weights of a network are computed once per SLAMNetwork.forward (one kernel for all layers,
+# ops.WeightNormFn) and shared by the sampler pass (detached), the main pass and the eikonal pass; the reference recomputes
+# them in every Linear's pre-forward hook.  Outside of such a scope every call computes its own.
+_WB_SCOPE = None      # dict id(module) -> (list of [W, b, ...], made under grad mode?)  while a scope is open
+
+
+class weight_scope:
+    def __enter__(self):
+        global _WB_SCOPE
+        self.prev, _WB_SCOPE = _WB_SCOPE, {}
+        return self
+
+    def __exit__(self, *a):
+        global _WB_SCOPE
+        _WB_SCOPE = self.prev
+
+
 def _effective_wb(mod, n_lin, weight_norm):
+    lins = [getattr(mod, f"lin{l}") for l in range(n_lin)]
+    if not weight_norm:
+        out = []
+        for lin in lins:
+            out += [lin.weight, lin.bias]
+        return out
+    grad = torch.is_grad_enabled()
+    hit = _WB_SCOPE.get(id(mod)) if _WB_SCOPE is not None else None
+    if hit is not None and (hit[1] or not grad):
+        return hit[0] if grad else [t.detach() for t in hit[0]]
+    vg = []
+    for lin in lins:
+        vg += [lin.weight_v, lin.weight_g.reshape(-1)]
+    ws = ops.WeightNormFn.apply(*vg)
     out = []
-    for l in range(n_lin):
-        lin = getattr(mod, f"lin{l}")
-        w = torch._weight_norm(lin.weight_v, lin.weight_g, 0) if weight_norm else lin.weight
+    for w, lin in zip(ws, lins):
         out += [w, lin.bias]
+    if _WB_SCOPE is not None:
+        _WB_SCOPE[id(mod)] = (out, grad)
     return out
 
 
@@ -129,8 +160,11 @@ class ImplicitNetworkGrid(nn.Module):
         self._meta = ops.SdfMeta(self.encoding.grid_meta(divide_factor), multires, n_hidden, dims[-1]) if self.fused else None
 
     # ---- fused path plumbing
+    def effective_wb(self):
+        return _effective_wb(self, self.num_layers - 1, self.weight_norm)
+
     def fused_args(self):
-        return self._meta, self.encoding.embeddings, self.encoding.offsets, _effective_wb(self, self.num_layers - 1, self.weight_norm)
+        return self._meta, self.encoding.embeddings, self.encoding.offsets, self.effective_wb()
 
     def _fused_outputs(self, x, want_feat):
         meta, table, offsets, wb = self.fused_args()
@@ -248,6 +282,9 @@ class RenderingNetwork(nn.Module):
             and feature_vector_size <= ops.HIDDEN)
         self._n_hidden, self._feature = n_hidden, feature_vector_size
 
+    def effective_wb(self):
+        return _effective_wb(self, self.num_layers - 1, self.weight_norm)
+
     def _meta(self, color_stage):
         grid = self.encoding.grid_meta(self.divide_factor) if self.use_grid_feature else ops.GridMeta(0, 2, 1, 0.0, 1.0)
         return ops.ColorMeta(grid, self.multires_view, self._feature, self._n_hidden, color_stage == "base")
@@ -256,7 +293,7 @@ class RenderingNetwork(nn.Module):
         if self.fused:
             table = self.encoding.embeddings if self.use_grid_feature else None
             offsets = self.encoding.offsets if self.use_grid_feature else None
-            wb = _effective_wb(self, self.num_layers - 1, self.weight_norm)
+            wb = self.effective_wb()
             return ops.ColorNetFn.apply(points, view_dirs, normals, feature_vectors, table, offsets,
                                         self._meta(color_stage), *wb)
         # ---- layer-by-layer path for the other modes

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from .. import ops, parallel
 from ..utils import rend_util
 from ..utils.general import uv2patch
-from .base_networks import ImplicitNetworkGrid_COMBINE, RenderingNetwork
+from .base_networks import ImplicitNetworkGrid_COMBINE, RenderingNetwork, weight_scope
 from .density import GridPredefineDensity, LaplaceDensity
 from .ray_sampler import DeviceRng, ImportantSampler
 
@@ -88,6 +88,15 @@ class SLAMNetwork(nn.Module):
     # ------------------------------------------------------------------------------------------------
     def forward(self, input, indices, ground_truth, keyframe_list=None, frame_idx=-1, mode="vis", stage="fine",
                 color_stage="highfreq", iter=0):
+        with weight_scope():      # effective (weight-normed) weights: once per forward, shared by all passes
+            return self._forward(input, indices, ground_truth, keyframe_list, frame_idx, mode, stage, color_stage, iter)
+
+    def _forward(self, input, indices, ground_truth, keyframe_list, frame_idx, mode, stage, color_stage, iter):
+        if torch.is_grad_enabled():   # make them under grad mode before the (no-grad) sampler pass asks for them
+            nets = [self.implicit_network.coarse, self.rendering_network] + ([self.implicit_network.fine] if stage != "coarse" else [])
+            for net in nets:
+                if net.fused:
+                    net.effective_wb()
         if mode == "tracking":
             self.patchsizes = self.tracking_patchsizes
         elif mode == "mapping":

@@ -86,7 +86,30 @@ class ImportantSampler(RaySampler):
         self.scene_bounding_sphere = scene_bounding_sphere
         self.inverse_sphere_bg = False
 
+    def _get_z_vals_fused(self, ray_dirs, cam_loc, model):
+        """Two kernels around the SDF pass (csrc/sampler.cu): coarse depths + points, then one warp per ray for
+        weights -> pdf -> cdf -> inverse CDF -> merge -> sort -> eikonal pick."""
+        us = self.uniform_sampler
+        dev = ray_dirs.device
+        rng = getattr(model, "rng", None) or DeviceRng()
+        R, U = ray_dirs.shape[0], us.N_samples
+        with torch.no_grad():
+            rnd = rng.stratified((R, U), dev) if model.training else None
+            z_vals, far, points = ops.sampler_uniform(cam_loc.detach(), ray_dirs.detach(), us.near, us.far, us.scene_bounding_sphere,
+                                                      us.take_sphere_intersection, rnd, U)
+            sdf = model.implicit_network.get_sdf_vals(points)   # both nets, whatever the stage (ray_sampler.py:102)
+            sel = None
+            if self.N_samples_extra > 0:
+                sel = (rng.perm(U, self.N_samples_extra, dev) if model.training
+                       else torch.linspace(0, U - 1, self.N_samples_extra, device=dev).long())
+            S = self.N_samples + 2 + self.N_samples_extra
+            idx = rng.eik_index(S, R, dev)
+            return ops.sampler_resample(sdf, points, z_vals, model.voxels, self.N_samples, sel, us.near, far, idx)
+
     def get_z_vals(self, ray_dirs, cam_loc, model, frame_idx, keyframe_list, mode):
+        if (isinstance(model.density, GridPredefineDensity) and self.uniform_sampler.N_samples <= 1024
+                and self.N_samples + 2 + self.N_samples_extra <= 256):
+            return self._get_z_vals_fused(ray_dirs, cam_loc, model)
         z_vals, near, far = self.uniform_sampler.get_z_vals(ray_dirs, cam_loc, model)
         dev = z_vals.device
         rng = getattr(model, "rng", None) or DeviceRng()

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ColorNetT, GridT, LossT, OaJobT, SdfNetT
+from ._lib import ColorNetT, GridT, LossT, OaJobT, SdfNetT, WnJobT
 
 
 def lib():
@@ -213,6 +213,50 @@ class OuterAccumBatch:
         check(lib().nicer_outer_accum_batch(arr, len(self.jobs), self.P, stream()), "nicer_outer_accum_batch")
         _lib.launch_count += (len(self.jobs) + 7) // 8 - 1
         self.jobs, self.keep = [], []
+
+
+# --------------------------------------------------------------------------------------------- weight norm
+class WeightNormFn(torch.autograd.Function):
+    """(v_0, g_0, v_1, g_1, ...) -> (W_0, W_1, ...): the weight_norm reparametrisation of every Linear of one network
+    (torch._weight_norm(v, g, 0), base_networks.py:149-153) in one launch per direction."""
+
+    @staticmethod
+    def _jobs(vs, gs, ws=None, norms=None, dws=None, dvs=None, dgs=None):
+        arr = (WnJobT * len(vs))()
+        for i, (v, g) in enumerate(zip(vs, gs)):
+            j = arr[i]
+            j.v, j.g = ptr(v, name="weight_v").value, ptr(g, name="weight_g").value
+            j.rows, j.cols = v.shape[0], v.numel() // v.shape[0]
+            for name, lst in (("w", ws), ("norm", norms), ("dw", dws), ("dv", dvs), ("dg", dgs)):
+                if lst is not None:
+                    setattr(j, name, ptr(lst[i], name=name).value)
+        return arr
+
+    @staticmethod
+    def forward(ctx, *vg):
+        vs = [_c(t.detach()) for t in vg[0::2]]
+        gs = [_c(t.detach()) for t in vg[1::2]]
+        ws = [torch.empty_like(v) for v in vs]
+        norms = [torch.empty(v.shape[0], device=v.device) for v in vs]
+        check(lib().nicer_weight_norm(WeightNormFn._jobs(vs, gs, ws=ws, norms=norms), len(vs), stream()), "nicer_weight_norm")
+        ctx.save_for_backward(*vs, *gs, *norms)
+        ctx.n = len(vs)
+        return tuple(ws)
+
+    @staticmethod
+    def backward(ctx, *dws):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        vs, gs, norms = saved[:n], saved[n:2 * n], saved[2 * n:]
+        dws = [_c(d) if d is not None else torch.zeros_like(v) for d, v in zip(dws, vs)]
+        dvs = [torch.empty_like(v) for v in vs]
+        dgs = [torch.empty_like(g) for g in gs]
+        check(lib().nicer_weight_norm_backward(WeightNormFn._jobs(vs, gs, norms=norms, dws=dws, dvs=dvs, dgs=dgs), n, stream()),
+              "nicer_weight_norm_backward")
+        out = []
+        for dv, dg in zip(dvs, dgs):
+            out += [dv, dg]
+        return tuple(out)
 
 
 # --------------------------------------------------------------------------------------------- SDF network
@@ -435,6 +479,36 @@ def sampler_weights(sdf, x, z, voxels):
     check(lib().nicer_sampler_weights(ptr(sdf), ptr(x), ptr(z), ptr(vox), vox.shape[0], R, S,
                                       ptr(w), stream()), "nicer_sampler_weights")
     return w
+
+
+def sampler_uniform(cam_loc, ray_dirs, near, far_cap, bound, use_cube, rnd, N):
+    """Coarse depths z [R,N], far [R,1] and the sample points [R*N,3] in one kernel (UniformSampler.get_z_vals)."""
+    cam_loc, ray_dirs, rnd = _c(cam_loc), _c(ray_dirs), _c(rnd)
+    R, dev = ray_dirs.shape[0], ray_dirs.device
+    z = torch.empty(R, N, device=dev)
+    far = torch.empty(R, 1, device=dev)
+    points = torch.empty(R * N, 3, device=dev)
+    check(lib().nicer_sampler_uniform(ptr(cam_loc), ptr(ray_dirs), float(near), float(far_cap), float(bound), int(bool(use_cube)),
+                                      ptr(rnd), R, N, ptr(z), ptr(far), ptr(points), stream()), "nicer_sampler_uniform")
+    return z, far, points
+
+
+def sampler_resample(sdf, points, z, voxels, N, sel, near, far, eik_idx):
+    """weights -> pdf -> cdf -> inverse CDF -> merge with near / far / z[:, sel] -> sort -> eikonal pick, one warp per ray
+    (ImportantSampler.get_z_vals after the SDF pass).  Returns (z_out [R, N+2+len(sel)], z_eik [R,1])."""
+    R, U = z.shape
+    dev = z.device
+    n_extra = 0 if sel is None else int(sel.shape[0])
+    z_out = torch.empty(R, N + 2 + n_extra, device=dev)
+    z_eik = torch.empty(R, 1, device=dev)
+    sdf, points, z, vox, far = _c(sdf.reshape(-1)), _c(points), _c(z), _c(voxels), _c(far.reshape(-1))
+    sel = _c(sel.to(torch.int64)) if sel is not None else None
+    eik_idx = _c(eik_idx.to(torch.int64))
+    check(lib().nicer_sampler_resample(ptr(sdf), ptr(points), ptr(z), ptr(vox), vox.shape[0], R, U, N,
+                                       ptr(sel, torch.int64, "sel"), n_extra, float(near), ptr(far),
+                                       ptr(eik_idx, torch.int64, "eik_idx"), ptr(z_out), ptr(z_eik), None, stream()),
+          "nicer_sampler_resample")
+    return z_out, z_eik
 
 
 def voxel_count(x, voxels):

@@ -6,6 +6,7 @@
 // and raises if it is missing; tests/conftest.py swaps the handle explicitly for the CPU tests.
 #include <stdarg.h>
 #include <stdio.h>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/nicer_b200.h"
@@ -13,6 +14,7 @@
 #include "../../nicer_slam_b200/csrc/geometry_math.cuh"
 #include "../../nicer_slam_b200/csrc/loss_math.cuh"
 #include "../../nicer_slam_b200/csrc/warp_math.cuh"
+#include "../../nicer_slam_b200/csrc/sampler_math.cuh"
 #include "../../nicer_slam_b200/csrc/composite_math.cuh"
 
 using namespace nicer;
@@ -201,6 +203,80 @@ extern "C" int nicer_sampler_weights(const float *sdf, const float *x, const flo
                                      uint32_t res, uint32_t R, uint32_t S, float *weights, void *st) {
     return nicer_composite_forward(sdf, x, z, nullptr, nullptr, voxels, res, R, S, weights, nullptr, nullptr, nullptr,
                                    nullptr, st);
+}
+
+// ---------------------------------------------------------------------------------------------- weight norm
+extern "C" int nicer_weight_norm(const nicer_wn_job_t *jobs, uint32_t n, void *) {
+    for (uint32_t k = 0; k < n; ++k) {
+        const nicer_wn_job_t &J = jobs[k];
+        for (uint32_t r = 0; r < J.rows; ++r) {
+            const float *v = J.v + (size_t)r * J.cols;
+            float ss = 0.f;
+            for (uint32_t c = 0; c < J.cols; ++c) ss += v[c] * v[c];
+            const float nrm = sqrtf(ss), s = J.g[r] / nrm;
+            for (uint32_t c = 0; c < J.cols; ++c) J.w[(size_t)r * J.cols + c] = v[c] * s;
+            if (J.norm) J.norm[r] = nrm;
+        }
+    }
+    return 0;
+}
+extern "C" int nicer_weight_norm_backward(const nicer_wn_job_t *jobs, uint32_t n, void *) {
+    for (uint32_t k = 0; k < n; ++k) {
+        const nicer_wn_job_t &J = jobs[k];
+        for (uint32_t r = 0; r < J.rows; ++r) {
+            const float *v = J.v + (size_t)r * J.cols, *dw = J.dw + (size_t)r * J.cols;
+            float dot = 0.f;
+            for (uint32_t c = 0; c < J.cols; ++c) dot += dw[c] * v[c];
+            const float nrm = J.norm[r], a = J.g[r] / nrm, b = dot / (nrm * nrm);
+            for (uint32_t c = 0; c < J.cols; ++c) J.dv[(size_t)r * J.cols + c] = a * (dw[c] - v[c] * b);
+            J.dg[r] = dot / nrm;
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- hierarchical sampler
+extern "C" int nicer_sampler_uniform(const float *cam_loc, const float *ray_dirs, float near, float far_cap, float bound, int use_cube,
+                                     const float *rnd, uint32_t R, uint32_t N, float *z, float *far_out, float *points, void *) {
+    for (uint32_t r = 0; r < R; ++r) {
+        const float far = use_cube ? cube_far(cam_loc + 3 * r, ray_dirs + 3 * r, bound, far_cap) : far_cap;
+        if (far_out) far_out[r] = far;
+        for (uint32_t i = 0; i < N; ++i) {
+            const size_t e = (size_t)r * N + i;
+            z[e] = uniform_z(near, far, N, i, rnd != nullptr, rnd ? rnd[e] : 0.f);
+            if (points)
+                for (int a = 0; a < 3; ++a) points[3 * e + a] = cam_loc[3 * r + a] + fmul_exact(z[e], ray_dirs[3 * r + a]);
+        }
+    }
+    return 0;
+}
+
+extern "C" int nicer_sampler_resample(const float *sdf, const float *x, const float *z, const float *voxels, uint32_t res,
+                                      uint32_t R, uint32_t U, uint32_t N, const int64_t *sel, uint32_t n_extra, float near,
+                                      const float *far, const int64_t *eik_idx, float *z_out, float *z_eik, float *weights,
+                                      void *st) {
+    std::vector<float> w((size_t)R * U);
+    nicer_composite_forward(sdf, x, z, nullptr, nullptr, voxels, res, R, U, w.data(), nullptr, nullptr, nullptr, nullptr, st);
+    const uint32_t S = N + 2 + n_extra;
+    std::vector<float> cdf(U), srt(S);
+    for (uint32_t r = 0; r < R; ++r) {
+        const float *wr = w.data() + (size_t)r * U, *zr = z + (size_t)r * U;
+        if (weights) memcpy(weights + (size_t)r * U, wr, sizeof(float) * U);
+        float tot = 0.f;
+        for (uint32_t i = 0; i + 1 < U; ++i) tot += wr[i] + 1e-5f;
+        cdf[0] = 0.f;
+        float run = 0.f;
+        for (uint32_t i = 0; i + 1 < U; ++i) { run += (wr[i] + 1e-5f) / tot; cdf[i + 1] = run; }
+        cdf[U - 1] = std::min(cdf[U - 1], 1.0f);      // see sampler.cu: the outcome of exact arithmetic at u = 1
+        for (uint32_t k = 0; k < N; ++k) srt[k] = invert_cdf(cdf.data(), zr, U, linspace_at(0.f, 1.f, N, k));
+        srt[N] = near;
+        srt[N + 1] = far[r];
+        for (uint32_t j = 0; j < n_extra; ++j) srt[N + 2 + j] = zr[(uint32_t)sel[j]];
+        std::sort(srt.begin(), srt.end());
+        memcpy(z_out + (size_t)r * S, srt.data(), sizeof(float) * S);
+        if (z_eik) z_eik[r] = srt[(uint32_t)eik_idx[r]];
+    }
+    return 0;
 }
 
 extern "C" int nicer_composite_backward(const float *sdf, const float *x, const float *z, const float *rgb,
