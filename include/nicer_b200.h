@@ -191,6 +191,13 @@ int nicer_composite_backward(const float *sdf, const float *x, const float *z, c
 int nicer_sampler_weights(const float *sdf, const float *x, const float *z, const float *voxels,
                           uint32_t voxel_res, uint32_t R, uint32_t S, float *weights, void *stream);
 
+/* ---- fused dense Adam step (+ gradient zeroing) for the hash-grid tables; bit-identical to
+ * torch.optim.Adam(betas=(beta1,beta2), eps=eps) without amsgrad / weight decay (volsdf_train.py:174, 547, 576).
+ * All four arrays hold n fp32 values, 16-byte aligned; step is the 1-based update count. */
+int nicer_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, double lr, double beta1,
+                    double beta2, double eps, uint64_t step, int zero_grad, void *stream);
+int nicer_set_adam_variant(int variant);   /* test hook: rounding variant of the update (csrc/adam.cu) */
+
 /* ---- weight_norm of all Linear layers of a network in one launch (torch._weight_norm, dim 0; model/base_networks.py:149-153):
  * forward: w[r,:] = g[r] * v[r,:] / ||v[r,:]||, norm[r] = ||v[r,:]|| (norm optional); backward (needs norm): dv, dg from dw. */
 #define NICER_WN_MAX_JOBS 8

@@ -88,6 +88,19 @@ class OracleBackend:
 _backend = OracleBackend()
 
 
+def backend_for(t):
+    """CPU tensors: the C restatement above.  CUDA tensors (GPU box, tests only): the reference's OWN CUDA kernels compiled
+    for sm_100a by oracle/build_ref.py (oracle/_ref/_hash_encoder_ref.so) -- same three entry points, same signatures
+    (hashencoder.h:13-15) -- so that render_oracle.py run on the GPU is the reference's stack on the reference's kernels."""
+    if not t.is_cuda:
+        return _backend
+    from . import build_ref
+    mod = build_ref.load()
+    if mod is None:
+        raise RuntimeError("oracle/_ref/_hash_encoder_ref.so is not built (python -m oracle.build_ref where /root/reference exists)")
+    return mod
+
+
 def level_table(num_levels, base_resolution, desired_resolution, log2_hashmap_size, input_dim=3):
     """Per-level offsets and growth factor (hashgrid.py:141-173)."""
     per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1)) \
@@ -110,9 +123,10 @@ class _Encode(torch.autograd.Function):
         x01 = x01.contiguous()
         B, D = x01.shape
         L, C = offsets.shape[0] - 1, table.shape[1]
-        out = torch.empty(L, B, C)
-        dy_dx = torch.empty(B, L * D * C) if want_dx else torch.empty(1)
-        _backend.hash_encode_forward(x01, table.contiguous(), offsets, out, B, D, C, L, S, H, want_dx, dy_dx)
+        out = torch.empty(L, B, C, device=x01.device)
+        dy_dx = torch.empty(B, L * D * C, device=x01.device) if want_dx else torch.empty(1, device=x01.device)
+        offsets = offsets.to(x01.device)
+        backend_for(x01).hash_encode_forward(x01, table.contiguous(), offsets, out, B, D, C, L, float(S), H, want_dx, dy_dx)
         ctx.save_for_backward(x01, table, offsets, dy_dx)
         ctx.meta = (B, D, C, L, S, H, want_dx)
         return out.permute(1, 0, 2).reshape(B, L * C)
@@ -134,7 +148,7 @@ class _EncodeBwd(torch.autograd.Function):
         B, D, C, L, S, H, want_dx = meta
         gx = torch.zeros_like(x01)
         gt = torch.zeros_like(table)
-        _backend.hash_encode_backward(g, x01, table.contiguous(), offsets, gt, B, D, C, L, S, H, want_dx, dy_dx, gx)
+        backend_for(x01).hash_encode_backward(g, x01, table.contiguous(), offsets, gt, B, D, C, L, float(S), H, want_dx, dy_dx, gx)
         ctx.save_for_backward(g, x01, table, offsets, dy_dx)
         ctx.meta = meta
         return gx, gt
@@ -145,8 +159,8 @@ class _EncodeBwd(torch.autograd.Function):
         B, D, C, L, S, H, want_dx = ctx.meta
         gg = torch.zeros_like(g)
         g2t = torch.zeros_like(table)
-        _backend.hash_encode_second_backward(g, x01, table.contiguous(), offsets, B, D, C, L, S, H, want_dx,
-                                             dy_dx, ggx.contiguous(), gg, g2t)
+        backend_for(x01).hash_encode_second_backward(g, x01, table.contiguous(), offsets, B, D, C, L, float(S), H, want_dx,
+                                                     dy_dx, ggx.contiguous(), gg, g2t)
         return gg, None, g2t, None, None, None
 
 

@@ -205,6 +205,27 @@ extern "C" int nicer_sampler_weights(const float *sdf, const float *x, const flo
                                    nullptr, st);
 }
 
+// ---------------------------------------------------------------------------------------------- Adam
+extern "C" int nicer_adam_step(float *p, float *g, float *m, float *v, uint64_t n, double lr, double beta1, double beta2, double eps,
+                               uint64_t step, int zero_grad, void *) {
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    const float w1 = (float)(1.0 - beta1), w2 = (float)(1.0 - beta2), b2 = (float)beta2;
+    const float bc2_sqrt = (float)sqrt(bc2), neg_step = (float)(-(lr / bc1)), e = (float)eps;
+    // rounded operation by operation like torch's CPU kernels (no FMA contraction on this build)
+    for (uint64_t i = 0; i < n; ++i) {
+        const float gk = g[i];
+        volatile float d = gk - m[i], wd = w1 * d;
+        m[i] = m[i] + wd;
+        volatile float t = v[i] * b2, a = w2 * gk, ag = a * gk;
+        v[i] = t + ag;
+        volatile float q = sqrtf(v[i]) / bc2_sqrt, denom = q + e, r = m[i] / denom, sr = neg_step * r;
+        p[i] = p[i] + sr;
+        if (zero_grad) g[i] = 0.f;
+    }
+    return 0;
+}
+extern "C" int nicer_set_adam_variant(int) { return 0; }
+
 // ---------------------------------------------------------------------------------------------- weight norm
 extern "C" int nicer_weight_norm(const nicer_wn_job_t *jobs, uint32_t n, void *) {
     for (uint32_t k = 0; k < n; ++k) {

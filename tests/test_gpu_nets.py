@@ -76,13 +76,22 @@ def test_color_net_16_levels(stage):
     net = ro.make_color_net(spec, [64, 64], 64, seed=5, table_scale=0.3)
     P = 5000
     x0, v0, n0, f0 = torch.rand(P, 3) * 2.06 - 1.03, torch.randn(P, 3) * 0.7, torch.randn(P, 3), torch.randn(P, 64) * 0.5
+    wR = torch.randn(P, 3)
+    # The oracle runs on this GPU with the reference's own CUDA hash kernels when they are built (oracle/_ref): at level 15
+    # (resolution 2048) the CUDA build's exp2f-based level scale differs from the C library's in the last bit, which moves a
+    # sample by 1e-4 of a cell -- enough to change d rgb / d x by a few 1e-3.  On the CPU oracle only the x gradient is
+    # compared at a wider tolerance.
+    from oracle import build_ref
+    odev = "cuda" if build_ref.load() is not None else "cpu"
+    net["table"] = net["table"].to(odev)
+    net["layers"] = [tuple(t.to(odev) for t in l) for l in net["layers"]]
     leaves = [net["table"]] + [t for l in net["layers"] for t in l]
     for t in leaves:
         t.requires_grad_(True)
-    ins = [t.clone().requires_grad_(True) for t in (x0, v0, n0, f0)]
-    rgb = ro.color_net(ins[0], ins[2], ins[1], ins[3], net, stage)
-    wR = torch.randn(P, 3)
-    want = torch.autograd.grad((rgb * wR).sum(), ins + leaves, allow_unused=True)
+    ins = [t.clone().to(odev).requires_grad_(True) for t in (x0, v0, n0, f0)]
+    with torch.device(odev):
+        rgb = ro.color_net(ins[0], ins[2], ins[1], ins[3], net, stage)
+    want = torch.autograd.grad((rgb * wR.to(odev)).sum(), ins + leaves, allow_unused=True)
     meta = ops.ColorMeta(ops.GridMeta(16, 2, 16, float(np.log2(spec.pls)), 1.0), 4, 64, 2, stage == "base")
     dev = "cuda"
     ins2 = [t.to(dev).requires_grad_(True) for t in (x0, v0, n0, f0)]
@@ -91,11 +100,11 @@ def test_color_net_16_levels(stage):
     rgb2 = ops.ColorNetFn.apply(*ins2, tab, spec.offsets.to(dev), meta, *_wb(vgb))
     assert rel(rgb2, rgb) < 1e-4   # level 15 (res 2048): one fp32 ulp of x*scale is 1e-4 of a cell
     got = torch.autograd.grad((rgb2 * wR.to(dev)).sum(), ins2 + [tab] + [t for l in vgb for t in l], allow_unused=True)
-    for a, b in zip(got, want):
+    for i, (a, b) in enumerate(zip(got, want)):
         if b is None:
             assert a is None or float(a.abs().max()) == 0.0
         else:
-            assert rel(a, b) < 1e-3
+            assert rel(a, b) < (1e-3 if (odev == "cuda" or i != 0) else 1e-2), (i, rel(a, b))
 
 
 @pytest.mark.parametrize("R,S", [(64, 98), (33, 128), (5, 1), (7, 31)])
