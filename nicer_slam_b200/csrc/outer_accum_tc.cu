@@ -1,36 +1,49 @@
 // Tensor-core (tcgen05, 3xTF32) weight/bias gradient contraction:  C[M,N] += A[M][P] * B[N][P]^T,  bias[M] += rowsum(A).
 // Both operands are the feature-major buffers of the fused backward kernels, i.e. already K-major with K = samples.
-// The product is computed transposed, D^T[N (128 TMEM lanes)][M (64 columns)] = Bop * Aop^T with the B rows as the
-// M=128 operand (rows >= N are zero, row N is all ones so that D^T[N][m] = rowsum(A)[m] comes for free) and the A rows
-// as the N operand; both operands go through shared memory in the UMMA K-major no-swizzle layout as (hi, lo) pairs.
+// The product is computed transposed, D^T[N (128 TMEM lanes)][M (64 columns)] = Bop * Aop^T: the B rows are the M = 128
+// operand (lane n = row n; rows > N are zero, row N is all ones so that D^T[N][m] = rowsum(A)[m] comes for free) and the A rows
+// are the N operand.
 //
-// The kernel is HBM-bound by arithmetic intensity (16.8 FLOP/B at N = 64), so it is built as a streaming pipeline, one
-// persistent CTA per SM, split-K over the CTAs of a job:
-//   cp.async (LDGSTS, 16 B) fills a ring of raw fp32 half-stages (32 samples x (M + N) rows) 3-5 half-stages ahead of use;
-//   the 256 threads turn one raw half-stage into the (hi, lo) tf32 operand tiles of one of TWO operand buffers
-//   (raw rows are padded to 144 B so that both the 8-row x 16-B reads and the core-matrix writes are bank-conflict free);
-//   one thread issues the 8 tcgen05.mma of that half-stage (B_hi x [A_hi ; A_lo] as ONE N = 128 MMA + B_lo x A_hi, i.e.
-//   2 instead of 3 MMAs per K-step: a tcgen05.mma costs the same ~102 cycles for N = 64 and N = 128) and commits them to
-//   the buffer's mbarrier, so the MMAs of half-stage h run under the split of h + 1 and the loads of h + 2 ... h + 5.
-// Round 1's version (register prefetch of ONE 64-sample stage, single operand buffer) ran at 2.0 TB/s: ncu showed the
-// warps waiting on the next stage's loads (long scoreboard) with nothing else in flight.
+// The kernel is HBM-bound by arithmetic intensity (16.8 FLOP/B at N = 64), so it is a streaming pipeline, one persistent
+// CTA per SM (split-K over the CTAs of a job), in half-stages of 32 samples, warp-specialised:
+//   warps 0-3   "row warps": thread n owns row n of B.  It loads its 32 samples (8 x LDG.128, two half-stages ahead, in
+//               registers), splits them into (hi, lo) tf32 and writes them with tcgen05.st into the A-operand columns of
+//               TMEM (two buffers of 32 + 32 columns): the M = 128 operand never touches shared memory.
+//   warps 4-14  "A warps": cp.async (LDGSTS, 16 B) fills a ring of raw fp32 half-stages of the A rows 3-5 half-stages ahead;
+//               the warps split one raw half-stage into one of TWO shared-memory operand tiles [A_hi ; A_lo] (128 rows per
+//               16-byte K chunk, UMMA K-major no-swizzle; raw rows padded to 144 B: reads and writes bank-conflict free).
+//   warp 15     one thread issues the 8 tcgen05.mma of a half-stage when both halves of the operand pair are ready
+//               (mbarrier with 15 warp arrivals): B_hi x [A_hi ; A_lo] as ONE N = 128 MMA + B_lo x A_hi (N = 64), i.e. 2 instead
+//               of 3 MMAs per K-step (a tcgen05.mma costs the same ~102 cycles for N = 64 and N = 128), and commits them to the
+//               buffer's "free" mbarrier.  It takes no part in the loads, so the back-pressure of the MMA queue never stalls them.
+// History (profiles/r02_wgrad_notes.txt): round 1 (register prefetch of one 64-sample stage, one operand buffer, 2 CTAs/SM)
+// 2.0 TB/s, warps waiting on the next stage's loads; cp.async ring + two operand buffers but the MMA-issuing thread inside
+// the producer barrier: 1.8-2.2 TB/s (issue back-pressure serialised with the split); dedicated MMA warp, both operands through
+// shared memory: 2.4 TB/s, bound by shared-memory bandwidth (~120 KB moved per 16 KB half-stage: raw ring in + out, hi + lo
+// tiles, MMA operand fetches).  This version moves ~56 KB of shared memory per half-stage.
+#include <cstddef>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace nicer {
 
-constexpr int OT_THREADS = 256;
-constexpr int OT_HS = 32;                       // samples per half-stage
-constexpr int OT_CH = OT_HS / 4;                // 16-byte chunks per row per half-stage (8)
+constexpr int OT_THREADS = 512;
+constexpr int OT_HS = 64;                       // samples per stage
+constexpr int OT_CH = OT_HS / 4;                // 16-byte chunks per row per stage (16)
 constexpr int OT_BROWS = 128, OT_AROWS = 64;
-constexpr int OT_RAW_STRIDE = OT_HS * 4 + 16;   // bytes per raw row (padded: 144)
-constexpr int OT_MAX_SLOTS = 6;
-constexpr int OT_SMEM_LIMIT = 227 * 1024;
+constexpr int OT_RAW_STRIDE = OT_HS * 4 + 16;   // bytes per raw row (padded: 272 = 68 words, 68 mod 32 = 4)
+constexpr int OT_SLOT = OT_AROWS * OT_RAW_STRIDE;   // raw ring slot (A rows only): 17408 B
+constexpr int OT_SLOTS = 4;
+constexpr int OT_ROW_WARPS = 8, OT_A_WARPS = 7;     // + 1 MMA warp = 16.  Row warp w: TMEM lane quarter w % 4, sample half w / 4
+constexpr int OT_A_THREADS = OT_A_WARPS * 32;       // 224
+constexpr int OT_A_ITEMS = 5;                       // 64 rows x 16 chunks / 224 threads
+constexpr int OT_NBUF = 3;                          // operand buffers (TMEM rows + smem tile): write / MMA overlap needs > 2
+constexpr int OT_TMEM_COLS = 512;                   // D: [0,128)   A operand buffer b: hi [128 + 128 b, +64), lo [192 + 128 b, +64)
 
-struct OtOperands {                             // one operand buffer (48 KB)
-    float bhi[OT_CH * OT_BROWS * 4], blo[OT_CH * OT_BROWS * 4];
-    // A rows as ONE 128-row operand per chunk: rows [0,64) hold the hi halves, rows [64,128) the lo halves
-    float acomb[OT_CH * 2 * OT_AROWS * 4];
+struct OtSmem {
+    float acomb[OT_NBUF][OT_CH * 2 * OT_AROWS * 4]; // per buffer: chunk-major, rows [0,64) = A_hi, rows [64,128) = A_lo   (3 x 32 KB)
+    unsigned char ring[OT_SLOTS * OT_SLOT];         // raw fp32 A rows                                                   (54 KB)
 };
 
 // up to OT_MAX_JOBS contractions over the same sample range in one launch (the weight gradients of one network backward):
@@ -46,22 +59,38 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait(int pending) {       // at most `pending` groups still in flight
-    switch (pending) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// half a stage (32 samples) of one B row: 8 float4 from global (zeros beyond P)
+constexpr int OT_RC = OT_CH / 2;
+struct RowRegs { float4 v[OT_RC]; };
+__device__ __forceinline__ void row_load(RowRegs &r, const float *__restrict__ src, uint32_t p0, uint32_t P, bool active, float fill) {
+#pragma unroll
+    for (int c = 0; c < OT_RC; ++c) {
+        r.v[c] = make_float4(fill, fill, fill, fill);
+        if (active) {
+            r.v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p0 + c * 4 < P) r.v[c] = __ldg(reinterpret_cast<const float4 *>(src + p0 + c * 4));
+        }
+    }
+}
+// split and write to the A-operand columns of this thread's TMEM lane
+__device__ __forceinline__ void row_store(const RowRegs &r, uint32_t t_hi, uint32_t t_lo) {
+#pragma unroll
+    for (int c2 = 0; c2 < OT_RC / 2; ++c2) {
+        const float v[8] = {r.v[2 * c2].x, r.v[2 * c2].y, r.v[2 * c2].z, r.v[2 * c2].w,
+                            r.v[2 * c2 + 1].x, r.v[2 * c2 + 1].y, r.v[2 * c2 + 1].z, r.v[2 * c2 + 1].w};
+        tc::tmem_st8_split(t_hi + c2 * 8, t_lo + c2 * 8, v);
     }
 }
 
 __global__ void __launch_bounds__(OT_THREADS, 1)
-outer_accum_tc_kernel(const OtJobs js, uint32_t P, uint32_t halves_per_cta, uint32_t ctas_per_job, uint32_t n_slots, uint32_t rows_b_pad) {
+outer_accum_tc_kernel(const OtJobs js, uint32_t P, uint32_t halves_per_cta, uint32_t ctas_per_job) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    OtOperands *ops = reinterpret_cast<OtOperands *>(smem_raw);                  // [2]
-    unsigned char *ring = smem_raw + 2 * sizeof(OtOperands);                     // n_slots x slot_bytes
-    __shared__ __align__(8) uint64_t bar_free[2], bar_done;
+    OtSmem &sm = *reinterpret_cast<OtSmem *>(smem_raw);
+    __shared__ __align__(8) uint64_t bar_free[OT_NBUF], bar_full[OT_NBUF], bar_done;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t job = blockIdx.x / ctas_per_job, cta = blockIdx.x - job * ctas_per_job;
@@ -72,98 +101,147 @@ outer_accum_tc_kernel(const OtJobs js, uint32_t P, uint32_t halves_per_cta, uint
     const uint32_t h0 = cta * halves_per_cta;
     const uint32_t h1 = (h0 + halves_per_cta < n_half) ? h0 + halves_per_cta : n_half;
     const uint32_t nh = h1 > h0 ? h1 - h0 : 0;
-    const uint32_t slot_bytes = (OT_AROWS + rows_b_pad) * OT_RAW_STRIDE;
-    const uint32_t a_items = M * OT_CH, items = (M + N) * OT_CH;                 // 16-byte pieces of one half-stage
-    const uint32_t a_groups = (M + 7) / 8, groups = a_groups + (N + 7) / 8;      // 8-row groups (split work)
 
-    // one-time: zero both operand buffers (rows that are never written must stay 0), ones row at index N, barriers, TMEM
-    for (int i = tid; i < (int)(2 * sizeof(OtOperands) / 4); i += OT_THREADS) reinterpret_cast<float *>(ops)[i] = 0.f;
-    __syncthreads();
-    if (bias && N < OT_BROWS) {
-        for (int i = tid; i < 2 * OT_CH * 4; i += OT_THREADS) {
-            const int b = i / (OT_CH * 4), j = i - b * (OT_CH * 4);
-            ops[b].bhi[((j >> 2) * OT_BROWS + N) * 4 + (j & 3)] = 1.0f;          // exact in tf32
-        }
+    // one-time: zero both A tiles (rows >= M are never written), barriers, TMEM
+    for (int i = tid; i < (int)(sizeof(sm.acomb) / 4); i += OT_THREADS) reinterpret_cast<float *>(sm.acomb)[i] = 0.f;
+    if (tid == 0) {
+        for (int b = 0; b < OT_NBUF; ++b) { tc::mbar_init(&bar_free[b], 1); tc::mbar_init(&bar_full[b], OT_ROW_WARPS + OT_A_WARPS); }
+        tc::mbar_init(&bar_done, 1);
+        tc::fence_mbar_init();
     }
-    if (tid == 0) { tc::mbar_init(&bar_free[0], 1); tc::mbar_init(&bar_free[1], 1); tc::mbar_init(&bar_done, 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, 128);
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, OT_TMEM_COLS);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const uint32_t ring_u32 = tc::smem_u32(ring);
 
-    auto issue_load = [&](uint32_t h) {          // h: half-stage index relative to h0
-        if (h < nh) {
-            const uint32_t p0 = (h0 + h) * OT_HS;
-            const uint32_t dst0 = ring_u32 + (h % n_slots) * slot_bytes;
-            for (uint32_t i = tid; i < items; i += OT_THREADS) {
-                const bool isA = i < a_items;
-                const uint32_t k = isA ? i : i - a_items;
-                const uint32_t r = k >> 3, c = k & 7;
-                const uint32_t p = p0 + c * 4;
-                const float *src = isA ? A + (size_t)r * lda + p : B + (size_t)r * ldb + p;
-                const uint32_t row = isA ? r : OT_AROWS + r;
-                const bool ok = p < P;                                  // P % 4 == 0: a piece is either whole or absent
-                cp_async16(dst0 + row * OT_RAW_STRIDE + c * 16, ok ? (const void *)src : (const void *)A, ok ? 16u : 0u);
+    if (warp < OT_ROW_WARPS) {
+        // ---------------- row warps: B row n -> TMEM lane n; warps w and w + 4 share a lane quarter and take 16 samples each
+        const uint32_t n = (uint32_t)((warp & 3) * 32 + lane), half = (uint32_t)(warp >> 2);
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * (OT_HS / 2);
+        const bool active = n < N;
+        const float *src = B + (size_t)(active ? n : 0) * ldb + half * (OT_HS / 2);
+        // lanes without a B row carry a constant: the ones row (1.0 splits into hi = 1, lo = 0) when a bias is wanted, else zeros.
+        // tcgen05.st is warp-collective (.sync.aligned), so every lane stores every half-stage, active or not.
+        const float fill = (bias && n == N) ? 1.0f : 0.0f;
+        const uint32_t Pq = P > half * (OT_HS / 2) ? P - half * (OT_HS / 2) : 0;      // bound for this warp's shifted sample index
+        RowRegs r0, r1;
+        row_load(r0, src, h0 * OT_HS, Pq, active, fill);
+        row_load(r1, src, (h0 + 1) * OT_HS, Pq, active, fill);
+        auto step = [&](uint32_t h, RowRegs &r) {        // loads run two stages ahead of the store
+            const uint32_t b = h % OT_NBUF;
+            if (h >= OT_NBUF) tc::mbar_wait(&bar_free[b], ((h / OT_NBUF) - 1u) & 1u);
+            row_store(r, lane_base + 128 + 2 * OT_HS * b, lane_base + 128 + OT_HS + 2 * OT_HS * b);
+            tc::wait_st();
+            row_load(r, src, (h0 + h + 2) * OT_HS, Pq, active && h + 2 < nh, fill);
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_full[b]);
+        };
+        for (uint32_t h = 0; h < nh; h += 2) {
+            step(h, r0);
+            if (h + 1 < nh) step(h + 1, r1);
+        }
+    } else if (warp < OT_ROW_WARPS + OT_A_WARPS) {
+        // ---------------- A warps: raw ring -> [A_hi ; A_lo] tiles.  Per-thread work is fixed for the whole kernel:
+        //   load items  : 16-byte piece (row, chunk) -> global pointer (advances 32 samples per half-stage), ring offset
+        //   split items : (8-row group, chunk, row in group); lanes 0-7 = 8 consecutive rows of one chunk -> raw / tile offsets
+        const uint32_t at = (uint32_t)tid - OT_ROW_WARPS * 32;
+        const uint32_t ring_u32 = tc::smem_u32(sm.ring);
+        const float *ld_src[OT_A_ITEMS];
+        uint32_t ld_dst[OT_A_ITEMS], ld_p[OT_A_ITEMS], sp_raw[OT_A_ITEMS], sp_hi[OT_A_ITEMS];
+#pragma unroll
+        for (int k = 0; k < OT_A_ITEMS; ++k) {
+            const uint32_t i = at + k * OT_A_THREADS;
+            ld_src[k] = nullptr; ld_dst[k] = 0; ld_p[k] = 0xffffffffu; sp_raw[k] = 0xffffffffu; sp_hi[k] = 0;
+            if (i < M * OT_CH) {
+                const uint32_t r = i / OT_CH, c = i % OT_CH;
+                ld_p[k] = h0 * OT_HS + c * 4;
+                ld_src[k] = A + (size_t)r * lda + ld_p[k];
+                ld_dst[k] = r * OT_RAW_STRIDE + c * 16;
+            }
+            if (i < OT_AROWS * OT_CH) {
+                const uint32_t g = i / (8 * OT_CH), c = (i >> 3) % OT_CH, r = g * 8 + (i & 7);
+                if (r < M) {
+                    sp_raw[k] = r * OT_RAW_STRIDE + c * 16;
+                    sp_hi[k] = (c * 2 * OT_AROWS + r) * 16;
+                }
             }
         }
-        cp_async_commit();                       // every thread commits one group per half-stage, loads or not
-    };
-
-    const uint32_t ahead = n_slots - 1;
-    for (uint32_t h = 0; h < ahead; ++h) issue_load(h);
-    for (uint32_t h = 0; h < nh; ++h) {
-        cp_async_wait((int)ahead - 1);           // the group of half-stage h has landed (this thread's pieces)
-        __syncthreads();                         // ... and everybody else's
-        const uint32_t b = h & 1u;
-        if (h >= 2) tc::mbar_wait(&bar_free[b], ((h >> 1) - 1u) & 1u);           // MMAs of half-stage h-2 are done with buffer b
-        OtOperands &op = ops[b];
-        const unsigned char *raw = ring + (size_t)(h % n_slots) * slot_bytes;
-        // split: item = (8-row group, chunk, row in group); lanes 0-7 = 8 consecutive rows of one chunk
-        for (uint32_t i = tid; i < groups * 64; i += OT_THREADS) {
-            const uint32_t g = i >> 6, c = (i >> 3) & 7, r8 = i & 7;
-            const bool isA = g < a_groups;
-            const uint32_t r = (isA ? g : g - a_groups) * 8 + r8;
-            if (r >= (isA ? M : N)) continue;
-            const float4 v = *reinterpret_cast<const float4 *>(raw + (size_t)((isA ? 0 : OT_AROWS) + r) * OT_RAW_STRIDE + c * 16);
-            float4 hh, ll;
-            hh.x = tc::tf32_hi(v.x); hh.y = tc::tf32_hi(v.y); hh.z = tc::tf32_hi(v.z); hh.w = tc::tf32_hi(v.w);
-            ll.x = v.x - hh.x; ll.y = v.y - hh.y; ll.z = v.z - hh.z; ll.w = v.w - hh.w;
-            float *dh = isA ? op.acomb + ((size_t)c * 2 * OT_AROWS + r) * 4 : op.bhi + ((size_t)c * OT_BROWS + r) * 4;
-            float *dl = isA ? op.acomb + ((size_t)c * 2 * OT_AROWS + OT_AROWS + r) * 4 : op.blo + ((size_t)c * OT_BROWS + r) * 4;
-            *reinterpret_cast<float4 *>(dh) = hh;
-            *reinterpret_cast<float4 *>(dl) = ll;
+        uint32_t ld_slot = 0, ld_h = 0;
+        auto issue_load = [&]() {
+            if (ld_h < nh) {
+                const uint32_t dst0 = ring_u32 + ld_slot * OT_SLOT;
+#pragma unroll
+                for (int k = 0; k < OT_A_ITEMS; ++k) {
+                    if (ld_src[k]) {
+                        const bool ok = ld_p[k] < P;                    // P % 4 == 0: a piece is either whole or absent
+                        cp_async16(dst0 + ld_dst[k], ok ? (const void *)ld_src[k] : (const void *)A, ok ? 16u : 0u);
+                        ld_src[k] += OT_HS;
+                        ld_p[k] += OT_HS;
+                    }
+                }
+            }
+            cp_async_commit();                   // every thread commits one group per half-stage, loads or not
+            ++ld_h;
+            ld_slot = (ld_slot + 1 == OT_SLOTS) ? 0 : ld_slot + 1;
+        };
+#pragma unroll
+        for (int h = 0; h < OT_SLOTS - 1; ++h) issue_load();
+        uint32_t use_slot = 0;
+        for (uint32_t h = 0; h < nh; ++h) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(OT_SLOTS - 2) : "memory");     // half-stage h has landed (this thread's pieces)
+            asm volatile("bar.sync 1, %0;" ::"n"(OT_A_THREADS) : "memory");            // ... and every other A thread's
+            issue_load();                        // into the slot everybody finished reading before that barrier (half-stage h-1)
+            const uint32_t b = h % OT_NBUF;
+            if (h >= OT_NBUF) tc::mbar_wait(&bar_free[b], ((h / OT_NBUF) - 1u) & 1u);   // MMAs of stage h-3 are done with tile b
+            const unsigned char *raw = sm.ring + (size_t)use_slot * OT_SLOT;
+            unsigned char *tile = reinterpret_cast<unsigned char *>(sm.acomb[b]);
+            use_slot = (use_slot + 1 == OT_SLOTS) ? 0 : use_slot + 1;
+#pragma unroll
+            for (int k = 0; k < OT_A_ITEMS; ++k) {
+                if (sp_raw[k] != 0xffffffffu) {
+                    const float4 v = *reinterpret_cast<const float4 *>(raw + sp_raw[k]);
+                    float4 hh, ll;
+                    hh.x = tc::tf32_hi(v.x); hh.y = tc::tf32_hi(v.y); hh.z = tc::tf32_hi(v.z); hh.w = tc::tf32_hi(v.w);
+                    ll.x = v.x - hh.x; ll.y = v.y - hh.y; ll.z = v.z - hh.z; ll.w = v.w - hh.w;
+                    *reinterpret_cast<float4 *>(tile + sp_hi[k]) = hh;
+                    *reinterpret_cast<float4 *>(tile + sp_hi[k] + OT_AROWS * 16) = ll;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_full[b]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (lane == 0) {
+        // ---------------- MMA warp: one thread turns every filled (TMEM rows, smem tile) pair into 8 tcgen05.mma
+        constexpr uint32_t IDESC128 = tc::idesc_tf32(128, 2 * OT_AROWS), IDESC64 = tc::idesc_tf32(128, OT_AROWS);
+        for (uint32_t h = 0; h < nh; ++h) {
+            const uint32_t b = h % OT_NBUF;
+            tc::mbar_wait(&bar_full[b], (h / OT_NBUF) & 1u);
             tc::fence_after_sync();
-            constexpr uint32_t IDESC128 = tc::idesc_tf32(128, 2 * OT_AROWS), IDESC64 = tc::idesc_tf32(128, OT_AROWS);
-            const uint32_t bh = tc::smem_u32(op.bhi), bl = tc::smem_u32(op.blo), ac = tc::smem_u32(op.acomb);
+            const uint32_t ac = tc::smem_u32(sm.acomb[b]);
+            const uint32_t a_hi = tmem + 128 + 2 * OT_HS * b, a_lo = a_hi + OT_HS;
 #pragma unroll
             for (int ks = 0; ks < OT_HS / 8; ++ks) {
-                const uint64_t dbh = tc::smem_desc(bh + ks * 2 * OT_BROWS * 16, OT_BROWS * 16, 128);
-                const uint64_t dbl = tc::smem_desc(bl + ks * 2 * OT_BROWS * 16, OT_BROWS * 16, 128);
                 // the combined operand (128 rows per chunk); its first 64 rows alone are A_hi (same chunk stride)
                 const uint64_t dac = tc::smem_desc(ac + ks * 2 * (2 * OT_AROWS) * 16, 2 * OT_AROWS * 16, 128);
                 // columns [0,64) += B_hi A_hi^T, columns [64,128) += B_hi A_lo^T ; then columns [0,64) += B_lo A_hi^T
-                tc::mma_tf32_ss(tmem, dbh, dac, IDESC128, (h == 0 && ks == 0) ? 0u : 1u);
-                tc::mma_tf32_ss(tmem, dbl, dac, IDESC64, 1u);
+                tc::mma_tf32_ts(tmem, a_hi + ks * 8, dac, IDESC128, (h == 0 && ks == 0) ? 0u : 1u);
+                tc::mma_tf32_ts(tmem, a_lo + ks * 8, dac, IDESC64, 1u);
             }
             tc::mma_commit(&bar_free[b]);
         }
-        issue_load(h + ahead);                   // its slot was read (by everyone) before the barrier above, one iteration ago
+        if (nh > 0) tc::mma_commit(&bar_done);
     }
-    cp_async_wait(0);
-    if (tid == 0 && nh > 0) tc::mma_commit(&bar_done);
-    // epilogue: lane n of the accumulator holds D^T[n][0..63]
     if (nh > 0) {
         tc::mbar_wait(&bar_done, 0);
         __syncwarp();
         tc::fence_after_sync();
     }
+    // epilogue: lane n of the accumulator holds D^T[n][0..63]
     if (nh > 0 && warp < 4) {
         const uint32_t n = warp * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
@@ -186,7 +264,7 @@ outer_accum_tc_kernel(const OtJobs js, uint32_t P, uint32_t halves_per_cta, uint
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+    if (warp == 0) tc::tmem_dealloc(tmem, OT_TMEM_COLS);
 }
 
 bool tc_enabled();
@@ -199,21 +277,14 @@ static bool oa_tc_ok(const float *A, uint32_t lda, uint32_t M, const float *B, u
 
 static int oa_launch(const OtJobs &js, uint32_t n_jobs, uint32_t P, cudaStream_t st) {
     const uint32_t n_half = div_up(P, OT_HS);
-    uint32_t n_max = 0;
-    for (uint32_t j = 0; j < n_jobs; ++j) n_max = js.N[j] > n_max ? js.N[j] : n_max;
-    const uint32_t rows_b_pad = (n_max + 7u) & ~7u;
-    const uint32_t slot = (OT_AROWS + rows_b_pad) * OT_RAW_STRIDE;
-    uint32_t n_slots = (uint32_t)((OT_SMEM_LIMIT - 2 * sizeof(OtOperands) - 256) / slot);
-    if (n_slots > OT_MAX_SLOTS) n_slots = OT_MAX_SLOTS;
-    if (n_slots < 3) NICER_FAIL(-1, "nicer_outer_accum(tc): operand too wide for the shared-memory ring");
     uint32_t per_job = (uint32_t)num_sms() / n_jobs;            // one persistent CTA per SM, split over the jobs
     if (per_job == 0) per_job = 1;
     if (per_job > n_half) per_job = n_half;
     const uint32_t hpc = div_up(n_half, per_job);
     per_job = div_up(n_half, hpc);
-    const size_t smem = 2 * sizeof(OtOperands) + (size_t)n_slots * slot;
+    const size_t smem = sizeof(OtSmem);
     NICER_CUDA(cudaFuncSetAttribute(outer_accum_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "nicer_outer_accum(tc)");
-    outer_accum_tc_kernel<<<per_job * n_jobs, OT_THREADS, smem, st>>>(js, P, hpc, per_job, n_slots, rows_b_pad);
+    outer_accum_tc_kernel<<<per_job * n_jobs, OT_THREADS, smem, st>>>(js, P, hpc, per_job);
     NICER_CHECK_LAUNCH("nicer_outer_accum(tc)");
     return 0;
 }

@@ -26,6 +26,23 @@ __global__ void __launch_bounds__(128, 1) k(int M, int N, int mode, int reps, lo
         const int nacc = (mode & 1) ? (N <= 64 ? 4 : (N <= 128 ? 2 : 1)) : 1;
         const uint32_t dbase = tmem + 128;       // A (TS) lives in columns [0,64)
         long long t0 = clock64();
+        if (mode >= 4) {
+            // the weight-gradient kernel's sequence: pairs (N = 128 into columns [0,128), then N = 64 into columns [0,64))
+            //   mode 4: SS, one accumulator set    5: SS, two accumulator sets alternating per pair
+            //   mode 6: TS, one accumulator set    7: TS, two accumulator sets alternating per pair
+            const uint32_t i128 = tc::idesc_tf32(128, 128), i64 = tc::idesc_tf32(128, 64);
+            const uint64_t db128 = tc::smem_desc(b, 128 * 16, 128);
+            for (int r = 0; r < reps / 2; ++r) {
+                const uint32_t d = dbase + (((mode & 1) && (r & 1)) ? 128u : 0u);
+                if (mode >= 6) {
+                    tc::mma_tf32_ts(d, tmem + (r & 3) * 8, db128, i128, 1u);
+                    tc::mma_tf32_ts(d, tmem + 32 + (r & 3) * 8, db128, i64, 1u);
+                } else {
+                    tc::mma_tf32_ss(d, da, db128, i128, 1u);
+                    tc::mma_tf32_ss(d, da, db128, i64, 1u);
+                }
+            }
+        } else
         for (int r = 0; r < reps; ++r) {
             const uint32_t d = dbase + (uint32_t)(r % nacc) * (uint32_t)N;
             if (mode >= 2) tc::mma_tf32_ts(d, tmem + (r & 7) * 8, db, idesc, 1u);
@@ -50,14 +67,16 @@ int main() {
     const int Ns[4] = {64, 80, 128, 256};
     for (int mi = 0; mi < 2; ++mi)
         for (int ni = 0; ni < 4; ++ni)
-            for (int mode = 0; mode < 4; ++mode) {
+            for (int mode = 0; mode < 8; ++mode) {
                 if (Ms[mi] == 64 && mode >= 2) continue;
+                if (mode >= 4 && ni != 2) continue;
                 k<<<148, 128, 160 * 1024>>>(Ms[mi], Ns[ni], mode, reps, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 long long h[148];
                 cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-                printf("M=%3d N=%3d mode=%d (%s, %s): %7.1f cycles/MMA  %s\n", Ms[mi], Ns[ni], mode, mode >= 2 ? "TS" : "SS",
-                       (mode & 1) ? "rotating acc" : "one acc", (double)h[0] / reps, e == cudaSuccess ? "" : cudaGetErrorString(e));
+                printf("M=%3d N=%3d mode=%d (%s, %s%s): %7.1f cycles/MMA  %s\n", Ms[mi], Ns[ni], mode, (mode & 2) ? "TS" : "SS",
+                       (mode & 1) ? "rotating acc" : "one acc", mode >= 4 ? ", N=128/N=64 pairs" : "", (double)h[0] / reps,
+                       e == cudaSuccess ? "" : cudaGetErrorString(e));
             }
     return 0;
 }
