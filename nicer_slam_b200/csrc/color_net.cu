@@ -174,8 +174,8 @@ extern "C" int nicer_color_backward(const nicer_color_net_t *net, const float *x
     if (P == 0) return 0;
     if (!x || !view || !normals || !feat_fm || !rgb || !A_fm || !g_rgb || !grad_normals || !grad_feat_fm || !ZB || !OB)
         NICER_FAIL(-1, "nicer_color_backward: NULL pointer");
-    if (net->grid.table && !net->grid_detached && (!grad_table || !GY))
-        NICER_FAIL(-1, "nicer_color_backward: grad_table and GY required when the grid is not detached");
+    if (net->grid.table && !net->grid_detached && grad_table && !GY)
+        NICER_FAIL(-1, "nicer_color_backward: GY workspace required for the table gradient");
     {
         const int r = launch_color_backward_tc(net, x, view, normals, P, rgb, A_fm, DYDX, g_rgb, grad_x, grad_view, grad_normals,
                                                grad_feat_fm, grad_table, ZB, OB, GY, (cudaStream_t)stream,

@@ -118,6 +118,7 @@ grid_scatter_kernel(const nicer_grid_t g, const LevelScales ls, const float *__r
 // GY2 == NULL: first-order term only
 int launch_grid_scatter(const nicer_grid_t *g, const float *x, uint32_t P, const float *GY1, const float *GY2,
                         const float *g_grad, float *grad_table, cudaStream_t st) {
+    if (!grad_table) return 0;      // table gradient not wanted (pose-only tracking): no scatter at all
     if (P == 0) return 0;
     const LevelScales ls = host_level_scales(g->L, g->S, g->H);
     const dim3 grid(div_up(div_up(P, GS_RUN), GS_BLOCK), g->L);

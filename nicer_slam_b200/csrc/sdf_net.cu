@@ -199,7 +199,7 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
                                   float *AB, float *TAN, float *T0, float *GY, void *stream, void *scatter_stream) {
     if (int e = check_sdf_net(net, "nicer_sdf_backward")) return e;
     if (P == 0) return 0;
-    if (!x || !Z || !DYDX || !grad_table || !ZB || !QB || !AB || !TAN || !T0)
+    if (!x || !Z || !DYDX || !ZB || !QB || !AB || !TAN || !T0)      /* grad_table may be NULL: no table gradient wanted */
         NICER_FAIL(-1, "nicer_sdf_backward: a required pointer is NULL");
     if (net->n_hidden > 1 && !R) NICER_FAIL(-1, "nicer_sdf_backward: R required for n_hidden > 1");
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_backward: n_hidden > 3 not built");

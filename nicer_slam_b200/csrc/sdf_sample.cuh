@@ -45,6 +45,7 @@ struct SdfNetView {
 
 template <int C>
 NHD void scatter_entry(float *grad_table, const LevelInfo &li, uint32_t idx, const float v[C]) {
+    if (!grad_table) return;        // table gradient not wanted (pose-only tracking)
     float *p = grad_table + ((size_t)li.offset + idx) * C;
 #ifdef __CUDA_ARCH__
     if constexpr (C == 8) {

@@ -21,6 +21,25 @@ from .embedder import get_embedder
 # ops.WeightNormFn) and shared by the sampler pass (detached), the main pass and the eikonal pass; the reference recomputes
 # them in every Linear's pre-forward hook.  Outside of such a scope every call computes its own.
 _WB_SCOPE = None      # dict id(module) -> (list of [W, b, ...], made under grad mode?)  while a scope is open
+_DETACHED = False     # True inside detached_parameters(): networks hand detached tables / weights to the fused kernels
+
+
+class detached_parameters:
+    """Pose-only passes (tracking): the trainer steps the camera optimizer only and throws the model gradients
+    away (volsdf_train.py:406-446, :547), so the kernels are given parameters that require no gradient and skip the grid
+    scatter and the weight-gradient contractions altogether."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global _DETACHED
+        self.prev, _DETACHED = _DETACHED, (self.on or _DETACHED)
+        return self
+
+    def __exit__(self, *a):
+        global _DETACHED
+        _DETACHED = self.prev
 
 
 class weight_scope:
@@ -41,17 +60,21 @@ def _effective_wb(mod, n_lin, weight_norm):
         for lin in lins:
             out += [lin.weight, lin.bias]
         return out
-    grad = torch.is_grad_enabled()
+    grad = torch.is_grad_enabled() and not _DETACHED
     hit = _WB_SCOPE.get(id(mod)) if _WB_SCOPE is not None else None
     if hit is not None and (hit[1] or not grad):
         return hit[0] if grad else [t.detach() for t in hit[0]]
     vg = []
     for lin in lins:
         vg += [lin.weight_v, lin.weight_g.reshape(-1)]
-    ws = ops.WeightNormFn.apply(*vg)
+    if grad:
+        ws = ops.WeightNormFn.apply(*vg)
+    else:
+        with torch.no_grad():
+            ws = ops.WeightNormFn.apply(*vg)
     out = []
     for w, lin in zip(ws, lins):
-        out += [w, lin.bias]
+        out += [w, lin.bias if grad else lin.bias.detach()]
     if _WB_SCOPE is not None:
         _WB_SCOPE[id(mod)] = (out, grad)
     return out
@@ -164,7 +187,8 @@ class ImplicitNetworkGrid(nn.Module):
         return _effective_wb(self, self.num_layers - 1, self.weight_norm)
 
     def fused_args(self):
-        return self._meta, self.encoding.embeddings, self.encoding.offsets, self.effective_wb()
+        table = self.encoding.embeddings.detach() if _DETACHED else self.encoding.embeddings
+        return self._meta, table, self.encoding.offsets, self.effective_wb()
 
     def _fused_outputs(self, x, want_feat):
         meta, table, offsets, wb = self.fused_args()
@@ -292,6 +316,8 @@ class RenderingNetwork(nn.Module):
     def forward(self, points, normals, view_dirs, feature_vectors, indices, color_stage="base"):
         if self.fused:
             table = self.encoding.embeddings if self.use_grid_feature else None
+            if table is not None and _DETACHED:
+                table = table.detach()
             offsets = self.encoding.offsets if self.use_grid_feature else None
             wb = self.effective_wb()
             return ops.ColorNetFn.apply(points, view_dirs, normals, feature_vectors, table, offsets,

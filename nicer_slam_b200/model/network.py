@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from .. import ops, parallel
 from ..utils import rend_util
 from ..utils.general import uv2patch
-from .base_networks import ImplicitNetworkGrid_COMBINE, RenderingNetwork, weight_scope
+from .base_networks import ImplicitNetworkGrid_COMBINE, RenderingNetwork, detached_parameters, weight_scope
 from .density import GridPredefineDensity, LaplaceDensity
 from .ray_sampler import DeviceRng, ImportantSampler
 
@@ -63,6 +63,10 @@ class SLAMNetwork(nn.Module):
         # "explicit" = the caller shards (parallel.shard_batch / gather_outputs), only the voxel counter is synchronised here;
         # False = every rank is an independent replica
         self.ray_parallel = True
+        # mode="tracking": the trainer only steps the camera optimizer and zeroes the model gradients before they are ever
+        # used (volsdf_train.py:406-446, :547), so the pass runs with detached parameters -- no grid scatter, no weight-gradient
+        # contractions.  Set False to get the reference's (discarded) parameter gradients as well.
+        self.tracking_pose_only = True
         self._sync_density_voxels()
 
     def _sync_density_voxels(self):
@@ -88,11 +92,13 @@ class SLAMNetwork(nn.Module):
     # ------------------------------------------------------------------------------------------------
     def forward(self, input, indices, ground_truth, keyframe_list=None, frame_idx=-1, mode="vis", stage="fine",
                 color_stage="highfreq", iter=0):
-        with weight_scope():      # effective (weight-normed) weights: once per forward, shared by all passes
+        with weight_scope(), detached_parameters(mode == "tracking" and self.tracking_pose_only):
+            # effective (weight-normed) weights: once per forward, shared by all passes
             return self._forward(input, indices, ground_truth, keyframe_list, frame_idx, mode, stage, color_stage, iter)
 
     def _forward(self, input, indices, ground_truth, keyframe_list, frame_idx, mode, stage, color_stage, iter):
-        if torch.is_grad_enabled():   # make them under grad mode before the (no-grad) sampler pass asks for them
+        if torch.is_grad_enabled() and not (mode == "tracking" and self.tracking_pose_only):
+            # make them under grad mode before the (no-grad) sampler pass asks for them
             nets = [self.implicit_network.coarse, self.rendering_network] + ([self.implicit_network.fine] if stage != "coarse" else [])
             for net in nets:
                 if net.fused:

@@ -305,7 +305,9 @@ class SdfNetFn(torch.autograd.Function):
                 gf = pad
         gg = _c(g_grad) if g_grad is not None else None
         grad_x = torch.zeros(P, 3, device=dev) if ctx.needs_input_grad[0] else None
-        grad_table = torch.zeros_like(table)
+        # pose-only tracking (detached parameters): no table scatter, no weight-gradient contractions
+        need_table, need_w = ctx.needs_input_grad[1], any(ctx.needs_input_grad[5:])
+        grad_table = torch.zeros_like(table) if need_table else None
         ZB = torch.empty(n * HIDDEN, P, device=dev)
         QB, AB, TAN = torch.empty_like(ZB), torch.empty_like(ZB), torch.empty_like(ZB)
         T0 = torch.empty(meta.d_in, P, device=dev)
@@ -315,6 +317,9 @@ class SdfNetFn(torch.autograd.Function):
         check(lib().nicer_sdf_backward(C.byref(net), ptr(x), P, ptr(Z), ptr(R), ptr(DYDX), ptr(gs), ptr(gf), ptr(gg),
                                        ptr(grad_x), ptr(grad_table), ptr(ZB), ptr(QB), ptr(AB), ptr(TAN),
                                        ptr(T0), ptr(GY), stream(), _sptr(side)), "nicer_sdf_backward")
+        if not need_w:
+            _join(side, None, defer=False)
+            return (grad_x, grad_table, None, None, None, *([None] * len(wb)))
         grads = []
         oa = OuterAccumBatch()
         for l in range(n + 1):
@@ -394,17 +399,22 @@ class ColorNetFn(torch.autograd.Function):
         grad_view = torch.empty(P, 3, device=dev) if ctx.needs_input_grad[1] else None
         grad_normals = torch.empty(P, 3, device=dev)
         grad_feat_fm = torch.empty(meta.feature, P, device=dev)
-        scatter = ctx.has_grid and not meta.detached
+        has_gy = ctx.has_grid and not meta.detached
+        scatter = has_gy and ctx.needs_input_grad[4]
+        need_w = any(ctx.needs_input_grad[7:])
         grad_table = torch.zeros_like(table) if scatter else None
         ZB = torch.empty(n * HIDDEN, P, device=dev)
         OB = torch.empty(3, P, device=dev)
-        GY = torch.empty(meta.grid.L * meta.grid.C, P, device=dev) if scatter else None
+        GY = torch.empty(meta.grid.L * meta.grid.C, P, device=dev) if has_gy else None
         net = _color_struct(meta, table, offsets, wb)
         side = _scatter_stream(dev) if scatter else None
         check(lib().nicer_color_backward(C.byref(net), ptr(x), ptr(view), ptr(normals), ptr(feat_fm), P, ptr(rgb),
                                          ptr(A_fm), ptr(DYDX), ptr(g_rgb), ptr(grad_x), ptr(grad_view),
                                          ptr(grad_normals), ptr(grad_feat_fm), ptr(grad_table), ptr(ZB), ptr(OB),
                                          ptr(GY), stream(), _sptr(side)), "nicer_color_backward")
+        if not need_w:
+            _join(side, None, defer=False)
+            return (grad_x, grad_view, grad_normals, grad_feat_fm.t(), grad_table, None, None, *([None] * len(wb)))
         grads = []
         oa = OuterAccumBatch()
         for l in range(n + 1):

@@ -138,8 +138,10 @@ def load_step(name, device="cpu"):
     return t, meta
 
 
-def run_step(model, fx, meta, device, frozen_z=True, loss_weights=None):
-    """Runs product forward + loss + backward on a golden step fixture. Returns (outputs, loss dict, cam7 grad)."""
+def run_step(model, fx, meta, device, frozen_z=True, loss_weights=None, pose_only=False):
+    """Runs product forward + loss + backward on a golden step fixture. Returns (outputs, loss dict, cam7 grad).
+    pose_only=False: tracking passes also produce the (discarded) parameter gradients the reference computes."""
+    model.tracking_pose_only = pose_only
     from nicer_slam_b200.utils.general import get_camera_from_tensor
     mode, stage, color_stage = meta["mode"], meta["stage"], meta["color_stage"]
     bs, npix, frame_idx, _seed = [int(v) for v in fx["meta"]]

@@ -143,3 +143,17 @@ def test_free_running_sampler_close_to_reference():
     assert rel(out["z_vals"], fx["out.z_vals"]) < 2e-3
     assert rel(out["rgb_values"], fx["out.rgb_values"]) < 1e-4
     assert rel(out["depth_values"], fx["out.depth_values"]) < 1e-4
+
+
+def test_pose_only_tracking_matches_full_tracking():
+    """mode="tracking" with detached parameters (the default: no grid scatter, no weight-gradient work) gives the same
+    outputs, loss and pose gradient as the full pass, and leaves the parameter gradients unset."""
+    fx, meta = gu.load_step("step_tracking.npz")
+    with emulated_library():
+        model, _ = gu.build_model()
+        out_a, lo_a, gcam_a = gu.run_step(model, fx, meta, "cpu", frozen_z=True, pose_only=False)
+        assert any(p.grad is not None for p in model.parameters())
+        out_b, lo_b, gcam_b = gu.run_step(model, fx, meta, "cpu", frozen_z=True, pose_only=True)
+        assert all(p.grad is None for p in model.parameters())
+    assert torch.equal(out_a["rgb_values"], out_b["rgb_values"]) and float(lo_a["loss"]) == float(lo_b["loss"])
+    assert rel(gcam_b, gcam_a) < 1e-6
