@@ -191,6 +191,14 @@ int nicer_composite_backward(const float *sdf, const float *x, const float *z, c
 int nicer_sampler_weights(const float *sdf, const float *x, const float *z, const float *voxels,
                           uint32_t voxel_res, uint32_t R, uint32_t S, float *weights, void *stream);
 
+/* ---- optical-flow projection i -> j (model/network.py:153-165): flow[e,p] = pix(K_e * (w2c_e * (loc[i] + depth[i,p] * dirs[i,p]))) - uv[i,p]
+ * with i = idii[e]; w2c / K are those of the edge's target frame.  Backward accumulates into zeroed g_depth, g_dirs, g_loc, g_w2c. */
+int nicer_flow_project(const float *depth, const float *dirs, const float *loc, const float *w2c, const float *K, const float *uv,
+                       const int64_t *idii, uint32_t E, uint32_t n, float *flow, void *stream);
+int nicer_flow_project_backward(const float *depth, const float *dirs, const float *loc, const float *w2c, const float *K,
+                                const int64_t *idii, uint32_t E, uint32_t n, const float *g_flow, float *g_depth, float *g_dirs,
+                                float *g_loc, float *g_w2c, void *stream);
+
 /* ---- fused dense Adam step (+ gradient zeroing) for the hash-grid tables; bit-identical to
  * torch.optim.Adam(betas=(beta1,beta2), eps=eps) without amsgrad / weight decay (volsdf_train.py:174, 547, 576).
  * All four arrays hold n fp32 values, 16-byte aligned; step is the 1-based update count. */

@@ -68,6 +68,8 @@ _SIGS = {
     "nicer_composite_backward": [_fp] * 6 + [_u32, _u32, _u32] + [_fp] * 11,
     "nicer_sampler_weights": [_fp] * 4 + [_u32, _u32, _u32, _fp, _fp],
     "nicer_voxel_count": [_fp, _u32, _fp, _u32, _fp],
+    "nicer_flow_project": [_fp] * 7 + [_u32, _u32, _fp, _fp],
+    "nicer_flow_project_backward": [_fp] * 6 + [_u32, _u32] + [_fp] * 6,
     "nicer_adam_step": [_fp, _fp, _fp, _fp, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, _fp],
     "nicer_set_adam_variant": [C.c_int],
     "nicer_weight_norm": [C.POINTER(WnJobT), _u32, _fp],

@@ -150,15 +150,13 @@ class SLAMNetwork(nn.Module):
             normal_map = torch.sum(weights.unsqueeze(-1) * normals.reshape(-1, N_samples, 3), 1)
 
         rendered_depth = depth_values.unsqueeze(2)
-        surf = (cam_loc.unsqueeze(1) + rendered_depth * ray_dirs.unsqueeze(1)).reshape(bs, -1, 3).permute(0, 2, 1)
 
         output = {}
-        if "edges" in ground_truth:   # optical-flow projection i -> j (network.py:153-165)
+        if "edges" in ground_truth:   # optical-flow projection i -> j (network.py:153-165): one kernel per direction
             idii, idjj, _, _ = ground_truth["edges"]
             w2c = torch.linalg.inv_ex(pose[idjj])[0]     # inv_ex: no host-side error check (CUDA-graph safe)
-            cam_pts = w2c[:, :3, :3] @ surf[idii] + w2c[:, :3, 3:]
-            proj = (intrinsics[idjj][:, :3, :3] @ cam_pts).permute(0, 2, 1)
-            output["flow"] = proj[..., :2] / (proj[..., 2:] + 1e-8) - uv[idii]
+            output["flow"] = ops.FlowProjectFn.apply(depth_values.reshape(-1), ray_dirs, cam_loc.reshape(bs, num_pixels, 3)[:, 0],
+                                                     w2c, intrinsics[idjj], uv, idii)
 
         if self.use_warp_loss and ("vis" not in mode) and ("tracking" not in mode):
             output["warp_output"] = self._warp(uv, pose, intrinsics, rendered_depth, ground_truth, batch_size)

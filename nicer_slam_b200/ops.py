@@ -764,3 +764,33 @@ class WarpSampleFn(torch.autograd.Function):
                                                ptr(g_sampled), ptr(g_depth), ptr(g_dirs), ptr(g_loc), ptr(g_w2c), stream()),
               "nicer_warp_sample_backward")
         return g_depth, g_dirs, g_loc, g_w2c, None, None, None
+
+
+# --------------------------------------------------------------------------------------------- flow projection
+class FlowProjectFn(torch.autograd.Function):
+    """(depth [B*n], dirs [B*n,3], loc [B,3], w2c [E,4,4], K [E,4,4], uv [B,n,2], idii [E]) -> flow [E,n,2]
+    (network.py:153-165); differentiable w.r.t. depth, dirs, loc and w2c."""
+
+    @staticmethod
+    def forward(ctx, depth, dirs, loc, w2c, K, uv, idii):
+        depth, dirs, loc = _c(depth.detach().reshape(-1).float()), _c(dirs.detach().reshape(-1, 3)), _c(loc.detach())
+        w2c, K, uv, idii = _c(w2c.detach()), _c(K.detach()), _c(uv.detach()), _c(idii.to(torch.int64))
+        E, n = idii.shape[0], uv.shape[1]
+        flow = torch.empty(E, n, 2, device=depth.device)
+        check(lib().nicer_flow_project(ptr(depth), ptr(dirs), ptr(loc), ptr(w2c), ptr(K), ptr(uv), ptr(idii, torch.int64, "idii"), E, n,
+                                       ptr(flow), stream()), "nicer_flow_project")
+        ctx.save_for_backward(depth, dirs, loc, w2c, K, idii)
+        ctx.dims = (E, n)
+        return flow
+
+    @staticmethod
+    def backward(ctx, g_flow):
+        depth, dirs, loc, w2c, K, idii = ctx.saved_tensors
+        E, n = ctx.dims
+        g_flow = _c(g_flow)
+        g_depth, g_dirs = torch.zeros_like(depth), torch.zeros_like(dirs)
+        g_loc, g_w2c = torch.zeros_like(loc), torch.zeros_like(w2c)
+        check(lib().nicer_flow_project_backward(ptr(depth), ptr(dirs), ptr(loc), ptr(w2c), ptr(K), ptr(idii, torch.int64, "idii"), E, n,
+                                                ptr(g_flow), ptr(g_depth), ptr(g_dirs), ptr(g_loc), ptr(g_w2c), stream()),
+              "nicer_flow_project_backward")
+        return g_depth, g_dirs, g_loc, g_w2c, None, None, None

@@ -55,3 +55,31 @@ def uv2patch(uv, patchsize):
     gx, gy = torch.meshgrid(r, r, indexing="ij")
     grid = torch.stack([gx, gy], -1)[None, None]
     return uv[:, :, None, None, :] + grid
+
+
+def split_input(model_input, total_pixels, n_pixels=10000):
+    """Pieces of ``n_pixels`` pixels of a full-image input (utils/general.py:169-185 of the reference; no .cuda() hop: the
+    index lives where ``uv`` lives)."""
+    split = []
+    for indx in torch.split(torch.arange(total_pixels, device=model_input["uv"].device), n_pixels, dim=0):
+        data = model_input.copy()
+        data["uv"] = torch.index_select(model_input["uv"], 1, indx)
+        for k in ("object_mask", "depth", "gt_depth"):
+            if k in data:
+                data[k] = torch.index_select(model_input[k], 1, indx)
+        split.append(data)
+    return split
+
+
+def merge_output(res, total_pixels, batch_size):
+    """Inverse of split_input on the per-piece output dicts (utils/general.py:188-204)."""
+    model_outputs = {}
+    for entry in res[0]:
+        if res[0][entry] is None:
+            continue
+        if len(res[0][entry].shape) == 1:
+            model_outputs[entry] = torch.cat([r[entry].reshape(batch_size, -1, 1) for r in res], 1).reshape(batch_size * total_pixels)
+        else:
+            model_outputs[entry] = torch.cat([r[entry].reshape(batch_size, -1, r[entry].shape[-1]) for r in res], 1).reshape(
+                batch_size * total_pixels, -1)
+    return model_outputs

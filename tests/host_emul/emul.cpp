@@ -205,6 +205,45 @@ extern "C" int nicer_sampler_weights(const float *sdf, const float *x, const flo
                                    nullptr, st);
 }
 
+// ---------------------------------------------------------------------------------------------- flow projection
+extern "C" int nicer_flow_project(const float *depth, const float *dirs, const float *loc, const float *w2c, const float *K, const float *uv,
+                                  const int64_t *idii, uint32_t E, uint32_t n, float *flow, void *) {
+    for (uint32_t t = 0; t < E * n; ++t) {
+        const uint32_t e = t / n, p = t - e * n, i = (uint32_t)idii[e], ray = i * n + p;
+        float X[3];
+        for (int a = 0; a < 3; ++a) X[a] = loc[3 * i + a] + depth[ray] * dirs[3 * (size_t)ray + a];
+        const WarpProj pr = warp_project(X, w2c + 16 * e, K + 16 * e, 2.0f, 2.0f);
+        flow[2 * (size_t)t] = pr.proj[0] / pr.zden - uv[2 * (size_t)ray];
+        flow[2 * (size_t)t + 1] = pr.proj[1] / pr.zden - uv[2 * (size_t)ray + 1];
+    }
+    return 0;
+}
+extern "C" int nicer_flow_project_backward(const float *depth, const float *dirs, const float *loc, const float *w2c, const float *K,
+                                           const int64_t *idii, uint32_t E, uint32_t n, const float *g_flow, float *g_depth, float *g_dirs,
+                                           float *g_loc, float *g_w2c, void *) {
+    for (uint32_t t = 0; t < E * n; ++t) {
+        const uint32_t e = t / n, p = t - e * n, i = (uint32_t)idii[e], ray = i * n + p;
+        const float d = depth[ray];
+        float dir[3], X[3];
+        for (int a = 0; a < 3; ++a) { dir[a] = dirs[3 * (size_t)ray + a]; X[a] = loc[3 * i + a] + d * dir[a]; }
+        const float *Wt = w2c + 16 * e, *Kt = K + 16 * e;
+        const WarpProj pr = warp_project(X, Wt, Kt, 2.0f, 2.0f);
+        const float gu = g_flow[2 * (size_t)t], gv = g_flow[2 * (size_t)t + 1];
+        const float gproj[3] = {gu / pr.zden, gv / pr.zden, -(gu * pr.proj[0] + gv * pr.proj[1]) / (pr.zden * pr.zden)};
+        float gcam[3], gX[3];
+        for (int c = 0; c < 3; ++c) gcam[c] = Kt[c] * gproj[0] + Kt[4 + c] * gproj[1] + Kt[8 + c] * gproj[2];
+        for (int c = 0; c < 3; ++c) gX[c] = Wt[c] * gcam[0] + Wt[4 + c] * gcam[1] + Wt[8 + c] * gcam[2];
+        for (int a = 0; a < 3; ++a) {
+            for (int c = 0; c < 3; ++c) g_w2c[16 * e + 4 * a + c] += gcam[a] * X[c];
+            g_w2c[16 * e + 4 * a + 3] += gcam[a];
+            g_dirs[3 * (size_t)ray + a] += d * gX[a];
+            g_loc[3 * i + a] += gX[a];
+        }
+        g_depth[ray] += gX[0] * dir[0] + gX[1] * dir[1] + gX[2] * dir[2];
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- Adam
 extern "C" int nicer_adam_step(float *p, float *g, float *m, float *v, uint64_t n, double lr, double beta1, double beta2, double eps,
                                uint64_t step, int zero_grad, void *) {
