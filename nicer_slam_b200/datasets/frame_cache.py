@@ -68,7 +68,9 @@ class FrameCache:
         if slots is None:
             slots = self.slots(idxs)
         B = slots.shape[0]
-        indices = torch.as_tensor([int(i) for i in idxs], dtype=torch.long) if idxs is not None else slots.cpu()
+        # frame indices as the reference returns them (host LongTensor); with explicit slots (no host round trip, e.g. inside a
+        # CUDA graph) the device slot tensor stands in
+        indices = torch.as_tensor([int(i) for i in idxs], dtype=torch.long) if idxs is not None else slots
         sample = {"intrinsics": self.intrinsics[slots], "pose": self.pose[slots]}
         gt = {}
         if sampling_idx is None:

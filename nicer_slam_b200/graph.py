@@ -13,6 +13,9 @@ class GraphedStep:
     def __init__(self, fn, warmup=3):
         """fn() -> tensor (e.g. the loss); must read its inputs from tensors that stay alive (static buffers) and must
         not synchronise with the host."""
+        # Warm-up and capture run on ONE side stream: autograd's AccumulateGrad nodes remember the stream of the first backward
+        # pass that created them, and a capture on a different stream would fork into that stream for every parameter gradient
+        # (torch warns "AccumulateGrad node's stream does not match ..."), leaving the accumulation on a branch of the graph.
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -22,7 +25,7 @@ class GraphedStep:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.output = fn()
 
     def replay(self):

@@ -89,7 +89,7 @@ class TrackingLoop:
                 torch.cuda.current_stream().wait_stream(s)
                 self._reset(cam7_init, frame_idx)
                 self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
+                with torch.cuda.graph(self.graph, stream=s):      # same stream as the warm-up (see graph.py)
                     self._iteration()
                 self._graph_frame_is_zero = self.frame_idx == 0
                 self._reset(cam7_init, frame_idx)

@@ -84,6 +84,7 @@ def test_full_step_matches_reference_stack_on_gpu(name):
         RenderingNetwork.COLOR_GRID = saved
     gu.load_params(model, params_cpu)
     model = model.to(dev).train()
+    model.tracking_pose_only = False      # compare the parameter gradients of the tracking pass too (the reference computes them)
 
     host = bench.synth_inputs(R, frames, gen, H, W, with_flow=(mode == "mapping"))
     gt = {k: host[k].to(dev) for k in ("rgb", "mask", "depth", "normal", "gt_depth")}
@@ -170,10 +171,11 @@ def test_full_step_matches_reference_stack_on_gpu(name):
         g = named[gu.ref_name(pname)].grad
         assert g is not None, pname
         # MLP weight gradients are fp32 sums over all P samples on BOTH sides (cuBLAS sgemm in the oracle, fp32 TMEM accumulation
-        # of 3xTF32 products here) with mixed signs: at P = 262 144 (C3) the two summation orders themselves differ by
-        # sqrt(P) * eps * cancellation ~ 5e-4 .. 1e-3 (observed 1.01e-3 on coarse.lin1.weight_v, 1.00e-3 on coarse.lin0.weight_g,
-        # whose rows <dW[r], v[r]> / ||v[r]|| cancel further).  P <= 50 k cases and every grid / pose gradient hold 1e-3.
-        big = R * S > 100_000 and ".lin" in pname
+        # of 3xTF32 products here) of terms with mixed signs and 1/beta-amplified magnitudes: in the C3 case (P = 65 536, S = 128)
+        # the two fp32 summation orders themselves differ by ~1e-3 on two tensors (observed 1.01e-3 on coarse.lin1.weight_v and
+        # 1.00e-3 on coarse.lin0.weight_g, whose rows <dW[r], v[r]> / ||v[r]|| cancel further).  The C2 cases and every grid /
+        # pose gradient hold 1e-3.
+        big = S >= 128 and ".lin" in pname
         tol = 3e-3 if pname.endswith("weight_g") else (2e-3 if big else 1e-3)
         assert rel(g, leaf.grad) < tol, (pname, rel(g, leaf.grad))
     assert rel(cam_g.grad, cam_o.grad) < 1e-3
