@@ -152,6 +152,17 @@ def _fm(t):
     return tt if tt.is_contiguous() else tt.contiguous()
 
 
+def _zeros_like_many(tensors):
+    """Zero tensors shaped like ``tensors`` carved out of ONE flat buffer (one fill kernel instead of one per tensor)."""
+    sizes = [t.numel() for t in tensors]
+    flat = torch.zeros(sum(sizes), device=tensors[0].device, dtype=tensors[0].dtype)
+    out, off = [], 0
+    for t, n in zip(tensors, sizes):
+        out.append(flat[off:off + n].view(t.shape))
+        off += n
+    return out
+
+
 def _c(t):
     """Contiguous version of t (None stays None).  The result must be bound to a name that outlives the library call:
     a temporary passed as ``ptr(_c(t))`` would be freed before the (host-emulated) kernel reads it."""
@@ -322,9 +333,10 @@ class SdfNetFn(torch.autograd.Function):
             return (grad_x, grad_table, None, None, None, *([None] * len(wb)))
         grads = []
         oa = OuterAccumBatch()
+        zeros = _zeros_like_many(list(wb))         # dW_0, db_0, dW_1, ... in one buffer
         for l in range(n + 1):
             W = wb[2 * l]
-            dW, db = torch.zeros_like(W), torch.zeros(W.shape[0], device=dev)
+            dW, db = zeros[2 * l], zeros[2 * l + 1]
             if l == 0:
                 oa.add(ZB[:HIDDEN], H0, dW, db)
                 oa.add(QB[:HIDDEN], T0, dW)
@@ -417,9 +429,10 @@ class ColorNetFn(torch.autograd.Function):
             return (grad_x, grad_view, grad_normals, grad_feat_fm.t(), grad_table, None, None, *([None] * len(wb)))
         grads = []
         oa = OuterAccumBatch()
+        zeros = _zeros_like_many(list(wb))
         for l in range(n + 1):
             W = wb[2 * l]
-            dW, db = torch.zeros_like(W), torch.zeros(W.shape[0], device=dev)
+            dW, db = zeros[2 * l], zeros[2 * l + 1]
             if l == 0:
                 # input = [x, PE(view), normals (33) | feat (F) | grid]: the feature block reads feat_fm in place, the
                 # forward kernel only materialised the 33 + L*C other rows of H0
@@ -755,10 +768,8 @@ class WarpSampleFn(torch.autograd.Function):
         depth, dirs_p, loc_p, w2c, K, img = ctx.saved_tensors
         B, N, pp, H, W = ctx.dims
         dev = depth.device
-        g_depth = torch.zeros(B, N, device=dev)
+        g_depth, g_loc, g_w2c = _zeros_like_many([depth, loc_p, w2c])
         g_dirs = torch.empty_like(dirs_p)
-        g_loc = torch.zeros(B, 3, device=dev)
-        g_w2c = torch.zeros(B, 4, 4, device=dev)
         g_sampled = _c(g_sampled)
         check(lib().nicer_warp_sample_backward(ptr(depth), ptr(dirs_p), ptr(loc_p), ptr(w2c), ptr(K), ptr(img), B, N, pp, H, W,
                                                ptr(g_sampled), ptr(g_depth), ptr(g_dirs), ptr(g_loc), ptr(g_w2c), stream()),
@@ -788,8 +799,7 @@ class FlowProjectFn(torch.autograd.Function):
         depth, dirs, loc, w2c, K, idii = ctx.saved_tensors
         E, n = ctx.dims
         g_flow = _c(g_flow)
-        g_depth, g_dirs = torch.zeros_like(depth), torch.zeros_like(dirs)
-        g_loc, g_w2c = torch.zeros_like(loc), torch.zeros_like(w2c)
+        g_depth, g_dirs, g_loc, g_w2c = _zeros_like_many([depth, dirs, loc, w2c])
         check(lib().nicer_flow_project_backward(ptr(depth), ptr(dirs), ptr(loc), ptr(w2c), ptr(K), ptr(idii, torch.int64, "idii"), E, n,
                                                 ptr(g_flow), ptr(g_depth), ptr(g_dirs), ptr(g_loc), ptr(g_w2c), stream()),
               "nicer_flow_project_backward")
