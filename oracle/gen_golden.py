@@ -103,6 +103,21 @@ TINY = dict(
     sampler=dict(near=0.0, N_samples=12, N_samples_eval=40, N_samples_extra=6),
 )
 
+# The SHIPPED grid geometry and sampler of confs/runconf_demo_2.conf (:76-160; identical networks in the Replica / 7-Scenes
+# confs): coarse 4 x 8 @ 32^3, fine 8 x 4 32 -> 128 (logmap 19), color 16 x 2 16 -> 2048 with 2^19 entries per level (the
+# reference hard-codes 2^24 = 1 GB, base_networks.py:265-284; the 2^24 table is compared on the GPU box against the
+# reference's CUDA kernels instead, tests/test_gpu_ref_cuda.py, tests/test_gpu_shipped_shapes.py).  Small frames: the warp
+# block only samples them.  P = rays x S >= 8192 so that the tcgen05 weight-gradient kernel is on the compared path.
+SHIPPED = dict(
+    H=68, W=120, feature=64,
+    coarse=dict(L=4, C=8, base=32, end=32, logmap=19, hidden=[64]),
+    fine=dict(L=8, C=4, base=32, end=128, logmap=19, hidden=[64, 64, 64]),
+    color=dict(L=16, C=2, base=16, end=2048, logmap=19, hidden=[64, 64]),
+    sampler=dict(near=0.0, N_samples=64, N_samples_eval=640, N_samples_extra=32),
+)
+SHIPPED_C3 = dict(SHIPPED, sampler=dict(near=0.0, N_samples=94, N_samples_eval=640, N_samples_extra=32))
+SLICE = 1009        # table gradients of the shipped-shape fixtures: every SLICE-th row + the norm
+
 LOSS_W = dict(assign_scale_shift_init=True, warp_loss_weight=0.5, warp_loss_type="l1", rgb_loss="torch.nn.L1Loss",
               eikonal_weight=0.1, smooth_weight=0.005, depth_weight=0.1, normal_l1_weight=0.05,
               normal_cos_weight=0.05, flow_weight=0.001)
@@ -161,6 +176,11 @@ def make_params(t=TINY, seed=10):
     return params
 
 
+def make_params_voxels(t=TINY, seed=10):
+    gen = torch.Generator().manual_seed(seed + 4)
+    return torch.poisson(torch.full((64, 64, 64), 50.0), generator=gen)
+
+
 def load_params_into_reference(model, params):
     sd = {}
     for ours, theirs in (("coarse", "implicit_network.coarse"), ("fine", "implicit_network.fine"),
@@ -202,19 +222,19 @@ def synth_batch(t, bs, npix, seed):
     return K, cam7, uv, sidx, gt
 
 
-def gen_step(ref, mode, fname, bs, npix, frame_idx, stage, color_stage, seed):
-    t = TINY
+def gen_step(ref, mode, fname, bs, npix, frame_idx, stage, color_stage, seed, t=TINY, slim=False):
     params = make_params(t)
     model, ds = build_reference_model(ref, t)
     load_params_into_reference(model, params)
     model.train()
     K, cam7, uv, sidx, gt = synth_batch(t, bs, npix, seed)
     if mode == "mapping":
-        ii = torch.tensor([0, 1]); jj = torch.tensor([1, 0])
+        ii = torch.arange(bs - 1) if bs > 2 else torch.tensor([0, 1])
+        jj = ii + 1 if bs > 2 else torch.tensor([1, 0])
         gt["edges"] = (ii, jj, ii * 10, jj * 10)
         gen = torch.Generator().manual_seed(seed + 99)
-        gt["flow"] = torch.randn(2, npix, 2, generator=gen) * 3
-        gt["flow_mask"] = torch.rand(2, npix, generator=gen) > 0.3
+        gt["flow"] = torch.randn(len(ii), npix, 2, generator=gen) * 3
+        gt["flow_mask"] = torch.rand(len(ii), npix, generator=gen) > 0.3
     w = LOSS_W if mode == "mapping" else TRACK_W
     loss_mod = ref.loss.SLAMLoss(trainer=None, train_dataset=ds, scan_id=2, model=model, **w)
 
@@ -290,7 +310,7 @@ def gen_step(ref, mode, fname, bs, npix, frame_idx, stage, color_stage, seed):
     if "edges" in gt:
         blob["gt.edges"] = torch.stack(gt["edges"])
     blob.update({f"rng.{k}": v for k, v in rng.rec.items()})
-    blob["voxels_before"] = make_params(t)["voxels"]
+    blob["voxels_before"] = params2["voxels"].new_tensor(make_params_voxels(t))
     blob["voxels_after"] = model.voxels
     for k in ("rgb_values", "depth_values", "normal_map", "z_vals", "sdf", "weights", "rgb", "entropy", "depth_vals",
               "grad_theta", "grad_theta_nei", "flow"):
@@ -301,7 +321,12 @@ def gen_step(ref, mode, fname, bs, npix, frame_idx, stage, color_stage, seed):
         blob["out.warp_gt"], blob["out.warp_sampled"], blob["out.warp_mask"] = g_, s_, m_
     for k, v in lo_ref.items():
         blob[f"loss.{k}"] = torch.as_tensor(v).float()
-    blob.update({f"grad.{k}": v for k, v in grads.items()})
+    for k, v in grads.items():
+        if slim and k.endswith(".table"):       # big tables: strided rows + norm (the table itself is regenerated from its seed)
+            blob[f"gradslice.{k}"] = v[::SLICE].contiguous()
+            blob[f"gradnorm.{k}"] = v.double().norm().float()
+        else:
+            blob[f"grad.{k}"] = v
     blob["grad.cam7"] = cam_ref.grad
     blob["meta"] = torch.tensor([bs, npix, frame_idx, seed])
     np.savez_compressed(os.path.join(OUT, fname), **{k: _np(v) for k, v in blob.items()},
@@ -324,14 +349,24 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref = ref_shims.import_reference()
-    gen_hash(ref)
-    gen_step(ref, "tracking", "step_tracking.npz", bs=1, npix=96, frame_idx=3, stage="fine", color_stage="highfreq",
-             seed=21)
-    gen_step(ref, "mapping", "step_mapping.npz", bs=2, npix=64, frame_idx=5, stage="fine", color_stage="highfreq",
-             seed=22)
-    gen_step(ref, "mapping", "step_mapping_coarse_base.npz", bs=2, npix=48, frame_idx=5, stage="coarse",
-             color_stage="base", seed=23)
-    gen_pretrain()
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "tiny"):
+        gen_hash(ref)
+        gen_step(ref, "tracking", "step_tracking.npz", bs=1, npix=96, frame_idx=3, stage="fine", color_stage="highfreq",
+                 seed=21)
+        gen_step(ref, "mapping", "step_mapping.npz", bs=2, npix=64, frame_idx=5, stage="fine", color_stage="highfreq",
+                 seed=22)
+        gen_step(ref, "mapping", "step_mapping_coarse_base.npz", bs=2, npix=48, frame_idx=5, stage="coarse",
+                 color_stage="base", seed=23)
+        gen_pretrain()
+    if what in ("all", "shipped"):
+        # shipped shapes: 8 x 16 = 128 rays x 98 = 12 544 samples, 1 x 128 rays tracking, S = 128
+        gen_step(ref, "mapping", "step_c2_mapping.npz", bs=8, npix=16, frame_idx=5, stage="fine", color_stage="highfreq",
+                 seed=31, t=SHIPPED, slim=True)
+        gen_step(ref, "tracking", "step_c2_tracking.npz", bs=1, npix=128, frame_idx=3, stage="fine", color_stage="highfreq",
+                 seed=32, t=SHIPPED, slim=True)
+        gen_step(ref, "mapping", "step_c3_mapping.npz", bs=4, npix=24, frame_idx=5, stage="fine", color_stage="highfreq",
+                 seed=33, t=SHIPPED_C3, slim=True)
 
 
 if __name__ == "__main__":

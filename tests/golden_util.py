@@ -20,6 +20,18 @@ TINY = dict(  # must equal oracle.gen_golden.TINY
     color=dict(L=16, C=2, base=4, end=48, logmap=9, hidden=[64, 64]),
     sampler=dict(near=0.0, N_samples=12, N_samples_eval=40, N_samples_extra=6),
 )
+# must equal oracle.gen_golden.SHIPPED / SHIPPED_C3: the grid geometry and sampler of the shipped confs
+SHIPPED = dict(
+    H=68, W=120, feature=64,
+    coarse=dict(L=4, C=8, base=32, end=32, logmap=19, hidden=[64]),
+    fine=dict(L=8, C=4, base=32, end=128, logmap=19, hidden=[64, 64, 64]),
+    color=dict(L=16, C=2, base=16, end=2048, logmap=19, hidden=[64, 64]),
+    sampler=dict(near=0.0, N_samples=64, N_samples_eval=640, N_samples_extra=32),
+)
+SHIPPED_C3 = dict(SHIPPED, sampler=dict(near=0.0, N_samples=94, N_samples_eval=640, N_samples_extra=32))
+SLICE = 1009
+SHIPPED_STEPS = {"step_c2_mapping.npz": SHIPPED, "step_c2_tracking.npz": SHIPPED, "step_c3_mapping.npz": SHIPPED_C3}
+
 LOSS_W = dict(assign_scale_shift_init=True, warp_loss_weight=0.5, warp_loss_type="l1", rgb_loss="torch.nn.L1Loss",
               eikonal_weight=0.1, smooth_weight=0.005, depth_weight=0.1, normal_l1_weight=0.05,
               normal_cos_weight=0.05, flow_weight=0.001)
@@ -138,7 +150,7 @@ def load_step(name, device="cpu"):
     return t, meta
 
 
-def run_step(model, fx, meta, device, frozen_z=True, loss_weights=None, pose_only=False):
+def run_step(model, fx, meta, device, frozen_z=True, loss_weights=None, pose_only=False, t=TINY):
     """Runs product forward + loss + backward on a golden step fixture. Returns (outputs, loss dict, cam7 grad).
     pose_only=False: tracking passes also produce the (discarded) parameter gradients the reference computes."""
     model.tracking_pose_only = pose_only
@@ -167,8 +179,45 @@ def run_step(model, fx, meta, device, frozen_z=True, loss_weights=None, pose_onl
     finally:
         model.ray_sampler = saved_sampler
     w = loss_weights or (LOSS_W if mode == "mapping" else TRACK_W)
-    loss_mod = SLAMLoss(trainer=None, train_dataset=_DS(TINY["H"], TINY["W"]), scan_id=2, model=model, **w)
+    loss_mod = SLAMLoss(trainer=None, train_dataset=_DS(t["H"], t["W"]), scan_id=2, model=model, **w)
     lo = loss_mod(out, gt, list(range(bs)), frame_idx=frame_idx, stage=stage)
     model.zero_grad(set_to_none=True)
     lo["loss"].backward()
     return out, lo, cam7.grad
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def check_shipped_step(name, device, tol_out=1e-4, tol_grad=1e-3):
+    """Product step at a shipped shape against the fixture the unmodified reference wrote (oracle/gen_golden.py shipped):
+    renders / per-sample outputs, loss terms, MLP and pose gradients in full, table gradients on every SLICE-th row + norm."""
+    t = SHIPPED_STEPS[name]
+    fx, meta = load_step(name, device)
+    model, _ = build_model(t=t, device=device)
+    out, lo, gcam = run_step(model, fx, meta, device, frozen_z=True, t=t)
+    for k in ("rgb_values", "depth_values", "normal_map", "sdf", "weights", "rgb", "grad_theta", "grad_theta_nei", "flow"):
+        if "out." + k in fx:
+            assert rel(out[k], fx["out." + k]) < tol_out, (name, k, rel(out[k], fx["out." + k]))
+    for k in lo:
+        ref = float(fx["loss." + k])
+        tol = 2e-2 if k == "warp_loss" else 1e-3          # border pixels projected into their own frame: see test_gpu_step.py
+        assert abs(float(lo[k]) - ref) <= tol * max(abs(ref), 1e-3), (name, k, float(lo[k]), ref)
+    named = dict(model.named_parameters())
+    n_checked = 0
+    for k in fx:
+        if k.startswith("grad.") and k != "grad.cam7":
+            g = named[ref_name(k[5:])].grad
+            assert rel(g, fx[k]) < tol_grad, (name, k, rel(g, fx[k]))
+            n_checked += 1
+        elif k.startswith("gradslice."):
+            g = named[ref_name(k[10:])].grad
+            assert rel(g[::SLICE], fx[k]) < tol_grad, (name, k, rel(g[::SLICE], fx[k]))
+            gn, rn = float(g.double().norm()), float(fx["gradnorm." + k[10:]])
+            assert abs(gn - rn) <= tol_grad * rn, (name, k, gn, rn)
+            n_checked += 1
+    assert n_checked >= 20, n_checked
+    assert rel(gcam, fx["grad.cam7"]) < tol_grad, (name, rel(gcam, fx["grad.cam7"]))
+    assert torch.equal(model.voxels.cpu(), fx["voxels_after"].cpu())

@@ -157,3 +157,11 @@ def test_pose_only_tracking_matches_full_tracking():
         assert all(p.grad is None for p in model.parameters())
     assert torch.equal(out_a["rgb_values"], out_b["rgb_values"]) and float(lo_a["loss"]) == float(lo_b["loss"])
     assert rel(gcam_b, gcam_a) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["step_c2_tracking.npz"])
+def test_shipped_shape_step_host_emulation(name):
+    """The host layer + host-compiled device functions on a shipped-shape fixture written by the unmodified reference
+    (real grid geometry, 640-sample sampler pass, S = 98); the mapping / C3 fixtures run on the GPU (tests/test_gpu_step.py)."""
+    with emulated_library():
+        gu.check_shipped_step(name, "cpu")

@@ -42,6 +42,14 @@ def test_step_matches_reference_goldens_frozen_z(name):
     assert torch.equal(model.voxels.cpu(), fx["voxels_after"].cpu())
 
 
+@pytest.mark.parametrize("name", list(gu.SHIPPED_STEPS))
+def test_step_matches_reference_goldens_shipped_shapes(name):
+    """C2 mapping (8 x 16 rays x 98 = 12 544 samples), C2 tracking, C3-shaped (S = 128) steps with the real grid geometry
+    (coarse 4 x 8 @ 32^3, fine 8 x 4 32 -> 128, color 16 x 2 16 -> 2048 @ 2^19) against fixtures written by the UNMODIFIED
+    reference Python (oracle/gen_golden.py shipped); P >= 8192, so the tcgen05 weight-gradient kernel is on the path."""
+    gu.check_shipped_step(name, "cuda")
+
+
 def test_sampler_replays_reference_draws():
     fx, meta = gu.load_step("step_tracking.npz", "cuda")
     model, _ = gu.build_model(device="cuda")
