@@ -198,9 +198,23 @@ def check_shipped_step(name, device, tol_out=1e-4, tol_grad=1e-3):
     fx, meta = load_step(name, device)
     model, _ = build_model(t=t, device=device)
     out, lo, gcam = run_step(model, fx, meta, device, frozen_z=True, t=t)
+    n_rays = fx["out.z_vals"].shape[0]
     for k in ("rgb_values", "depth_values", "normal_map", "sdf", "weights", "rgb", "grad_theta", "grad_theta_nei", "flow"):
-        if "out." + k in fx:
-            assert rel(out[k], fx["out." + k]) < tol_out, (name, k, rel(out[k], fx["out." + k]))
+        if "out." + k not in fx:
+            continue
+        a, b = out[k], fx["out." + k]
+        if k in ("sdf", "rgb"):
+            # The LAST sample of a ray sits exactly on the cube face (ray_sampler.py:23-35), where the encoder's in/out test
+            # (hashencoder.cu:152) flips with one ulp of the ray direction (discontinuity ii): on a flipped ray
+            # the reference sees zero grid features at that one sample.  Its compositing weight is ~0, so renders, losses
+            # and gradients are compared in full; the per-sample tensors are compared without the far sample, and at most
+            # 2 % of the rays may have a flipped far sample.
+            assert a.shape[0] == n_rays and a.shape == b.shape       # [rays, S] / [rays, S, 3]
+            far_a, far_b = a[:, -1].reshape(n_rays, -1), b[:, -1].reshape(n_rays, -1)
+            flipped = ((far_a - far_b).abs().amax(1) > 1e-4 * max(1.0, float(b.abs().max()))).sum()
+            assert int(flipped) <= max(1, n_rays // 50), (name, k, "far samples flipped", int(flipped))
+            a, b = a[:, :-1], b[:, :-1]
+        assert rel(a, b) < tol_out, (name, k, rel(a, b))
     for k in lo:
         ref = float(fx["loss." + k])
         tol = 2e-2 if k == "warp_loss" else 1e-3          # border pixels projected into their own frame: see test_gpu_step.py
