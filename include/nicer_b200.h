@@ -279,6 +279,21 @@ int nicer_warp_sample_backward(const float *depth, const float *dirs, const floa
                                const float *img, uint32_t B, uint32_t N, uint32_t pp, uint32_t H, uint32_t W,
                                const float *g_sampled, float *g_depth, float *g_dirs, float *g_loc, float *g_w2c, void *stream);
 
+/* nicer_warp_gt: ground-truth colour / depth of the patch pixels in their own frame (model/network.py:226-246)
+ *   uvp [B,M,2] pixel coordinates, img [B,H,W,3], dep [B,H,W] -> gt_rgb [B,M,3], gt_depth [B,M] (1 outside the image),
+ *   inside [B,M] (uint8) */
+int nicer_warp_gt(const float *uvp, const float *img, const float *dep, uint32_t B, uint32_t M, uint32_t H, uint32_t W,
+                  float *gt_rgb, float *gt_depth, uint8_t *inside, void *stream);
+
+/* nicer_masked_l1_mean: mean |a - b| over the selected entries = torch.abs(a[mask] - b[mask]).mean(), the photometric-warp
+ * and optical-flow terms (model/loss.py:93-104,145-152).  a [n_mask*inner], mask [n_mask] (uint8, one per `inner` values),
+ * b [b_len] read as b[i % b_len] (b_len = n_mask*inner when not broadcast) -> out[0] = mean, out[1] = number of selected values.
+ * backward: g [1] = dL/dmean -> ga [n_mask*inner] (written; 0 on unselected entries). */
+int nicer_masked_l1_mean(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask, uint32_t inner,
+                         uint32_t b_len, float *out, void *stream);
+int nicer_masked_l1_mean_backward(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask, uint32_t inner,
+                                  uint32_t b_len, const float *out, const float *g, float *ga, void *stream);
+
 /* ---- camera / ray helpers (one kernel each; the reference runs them as ~200 elementwise kernels per iteration)
  * nicer_pose_from_cam7            <- get_camera_from_tensor / quad2rotation   utils/general.py:52-100
  *   cam7 [B,7] (quaternion w,x,y,z un-normalised, translation) -> pose [B,4,4] row-major c2w
@@ -287,9 +302,13 @@ int nicer_warp_sample_backward(const float *depth, const float *dirs, const floa
  *   backward: g_dirs [B,N,3], g_loc [B,3] | NULL -> g_pose [B,4,4] (written; uv and K get no gradient)
  * nicer_ray_points                <- points = cam_loc + z * dir, dirs repeated per sample   model/network.py:112-117
  *   cam_loc [R,3], dirs [R,3], z [R,S] -> points [R*S,3], dirs_flat [R*S,3] | NULL
- *   backward: g_points | NULL, g_dirs_flat | NULL ([R*S,3]) -> g_loc [R,3], g_dirs [R,3] (written; z gets no gradient) */
+ *   backward: g_points | NULL, g_dirs_flat | NULL ([R*S,3]) -> g_loc [R,3], g_dirs [R,3] (written; z gets no gradient)
+ * nicer_inv4x4                    <- torch.inverse(pose) (w2c of the flow and warp blocks)   model/network.py:157,171
+ *   A [B,4,4] -> Ai [B,4,4] (Gauss-Jordan, partial pivoting); backward: Ai, G = dL/dAi -> GA = -Ai^T G Ai^T (written) */
 int nicer_pose_from_cam7(const float *cam7, uint32_t B, float *pose, void *stream);
 int nicer_pose_from_cam7_backward(const float *cam7, const float *g_pose, uint32_t B, float *g_cam7, void *stream);
+int nicer_inv4x4(const float *A, uint32_t B, float *Ai, void *stream);
+int nicer_inv4x4_backward(const float *Ai, const float *G, uint32_t B, float *GA, void *stream);
 int nicer_camera_rays(const float *uv, const float *pose, const float *K, uint32_t B, uint32_t N, float *dirs,
                       float *cam_loc, void *stream);
 int nicer_camera_rays_backward(const float *uv, const float *pose, const float *K, uint32_t B, uint32_t N,

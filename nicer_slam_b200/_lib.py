@@ -79,8 +79,13 @@ _SIGS = {
     "nicer_set_tensor_cores": [C.c_int],
     "nicer_slam_loss": [C.POINTER(LossT), _fp, _fp, _fp, _fp],
     "nicer_warp_sample": [_fp] * 6 + [_u32] * 5 + [_fp, _fp, _fp],
+    "nicer_warp_gt": [_fp] * 3 + [_u32] * 4 + [_fp] * 4,
+    "nicer_masked_l1_mean": [_fp] * 3 + [_u32] * 3 + [_fp, _fp],
+    "nicer_masked_l1_mean_backward": [_fp] * 3 + [_u32] * 3 + [_fp] * 4,
     "nicer_warp_sample_backward": [_fp] * 6 + [_u32] * 5 + [_fp] * 6,
     "nicer_pose_from_cam7": [_fp, _u32, _fp, _fp],
+    "nicer_inv4x4": [_fp, _u32, _fp, _fp],
+    "nicer_inv4x4_backward": [_fp, _fp, _u32, _fp, _fp],
     "nicer_pose_from_cam7_backward": [_fp, _fp, _u32, _fp, _fp],
     "nicer_camera_rays": [_fp, _fp, _fp, _u32, _u32, _fp, _fp, _fp],
     "nicer_camera_rays_backward": [_fp, _fp, _fp, _u32, _u32, _fp, _fp, _fp, _fp],

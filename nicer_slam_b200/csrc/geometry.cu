@@ -1,6 +1,7 @@
 // Camera / ray helpers of the hot path as single kernels (math in geometry_math.cuh):
 //   nicer_pose_from_cam7(_backward)   <- get_camera_from_tensor / quad2rotation   utils/general.py:52-100
 //   nicer_camera_rays(_backward)      <- get_camera_params / lift                 utils/rend_util.py:68-93,107-129
+//   nicer_inv4x4(_backward)           <- torch.inverse(pose) of the flow / warp blocks   model/network.py:157,171
 //   nicer_ray_points(_backward)       <- points = cam_loc + z * dir and the per-sample view directions
 //                                        model/network.py:112-117 (and their sum-over-samples backward)
 // All tensors are tiny next to the network kernels; the point is the launch count (the reference issues ~200 elementwise
@@ -17,6 +18,15 @@ __global__ void pose_from_cam7_kernel(const float *__restrict__ cam7, uint32_t B
 __global__ void pose_from_cam7_backward_kernel(const float *__restrict__ cam7, const float *__restrict__ g_pose, uint32_t B, float *g_cam7) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) pose_from_cam7_backward(cam7 + 7 * (size_t)b, g_pose + 16 * (size_t)b, g_cam7 + 7 * (size_t)b);
+}
+
+__global__ void inv4x4_kernel(const float *__restrict__ A, uint32_t B, float *Ai) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) inv4x4(A + 16 * (size_t)b, Ai + 16 * (size_t)b);
+}
+__global__ void inv4x4_backward_kernel(const float *__restrict__ Ai, const float *__restrict__ G, uint32_t B, float *GA) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) inv4x4_backward(Ai + 16 * (size_t)b, G + 16 * (size_t)b, GA + 16 * (size_t)b);
 }
 
 __global__ void camera_rays_kernel(const float *__restrict__ uv, const float *__restrict__ pose, const float *__restrict__ K, uint32_t B,
@@ -130,6 +140,22 @@ extern "C" int nicer_pose_from_cam7_backward(const float *cam7, const float *g_p
     if (!cam7 || !g_pose || !g_cam7) NICER_FAIL(-1, "nicer_pose_from_cam7_backward: NULL pointer");
     pose_from_cam7_backward_kernel<<<div_up(B, 64), 64, 0, (cudaStream_t)stream>>>(cam7, g_pose, B, g_cam7);
     NICER_CHECK_LAUNCH("nicer_pose_from_cam7_backward");
+    return 0;
+}
+
+extern "C" int nicer_inv4x4(const float *A, uint32_t B, float *Ai, void *stream) {
+    if (B == 0) return 0;
+    if (!A || !Ai) NICER_FAIL(-1, "nicer_inv4x4: NULL pointer");
+    inv4x4_kernel<<<div_up(B, 32), 32, 0, (cudaStream_t)stream>>>(A, B, Ai);
+    NICER_CHECK_LAUNCH("nicer_inv4x4");
+    return 0;
+}
+
+extern "C" int nicer_inv4x4_backward(const float *Ai, const float *G, uint32_t B, float *GA, void *stream) {
+    if (B == 0) return 0;
+    if (!Ai || !G || !GA) NICER_FAIL(-1, "nicer_inv4x4_backward: NULL pointer");
+    inv4x4_backward_kernel<<<div_up(B, 32), 32, 0, (cudaStream_t)stream>>>(Ai, G, B, GA);
+    NICER_CHECK_LAUNCH("nicer_inv4x4_backward");
     return 0;
 }
 

@@ -73,4 +73,68 @@ NHD void camera_ray_backward(const float v[3], const float gd[3], float gv[3]) {
     for (int i = 0; i < 3; ++i) gv[i] = gd[i] / n - 2.0f * v[i] * vg / (n * n);
 }
 
+// 4x4 inverse by Gauss-Jordan elimination with partial pivoting (what torch.inverse / linalg.inv_ex do through LU with
+// partial pivoting; network.py:157,171 invert the c2w poses).  A, Ai row-major; a singular matrix gives inf / nan, as LU does.
+NHD void inv4x4(const float *A, float *Ai) {
+    float m[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { m[r][c] = A[4 * r + c]; m[r][4 + c] = (r == c) ? 1.0f : 0.0f; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int piv = k;
+        float best = fabsf(m[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < 4; ++r) {
+            const float a = fabsf(m[r][k]);
+            if (a > best) { best = a; piv = r; }
+        }
+#pragma unroll
+        for (int r = k + 1; r < 4; ++r) {
+            if (r == piv) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { const float t = m[k][c]; m[k][c] = m[r][c]; m[r][c] = t; }
+            }
+        }
+        const float inv = 1.0f / m[k][k];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[k][c] *= inv;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (r == k) continue;
+            const float f = m[r][k];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) m[r][c] -= f * m[k][c];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Ai[4 * r + c] = m[r][4 + c];
+}
+
+// dL/dA = -Ai^T G Ai^T   (G = dL/dAi)
+NHD void inv4x4_backward(const float *Ai, const float *G, float *GA) {
+    float T[16];     // T = Ai^T G
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a += Ai[4 * k + r] * G[4 * k + c];
+            T[4 * r + c] = a;
+        }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a += T[4 * r + k] * Ai[4 * c + k];
+            GA[4 * r + c] = -a;
+        }
+}
+
 }  // namespace nicer

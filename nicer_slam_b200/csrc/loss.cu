@@ -184,6 +184,55 @@ loss_finalize_kernel(const nicer_loss_t a, const double *acc, const float *maskf
     }
 }
 
+
+// ---- masked L1 mean: mean |a - b| over the entries whose mask is set (the photometric-warp and optical-flow terms,
+// model/loss.py:93-104,145-152 of the reference: torch.abs(x[mask] - y[mask]).mean()).  a, b: [n_mask * inner], mask: one byte
+// per `inner` consecutive values; b may be shorter than a (b_len values, repeated: the warp target is the same for every
+// target frame).  One block: the tensors are a few 100 k values, the reduction order is fixed (deterministic).
+constexpr int ML_BLOCK = 1024;
+__global__ void __launch_bounds__(ML_BLOCK)
+masked_l1_mean_kernel(const float *__restrict__ a, const float *__restrict__ b, const unsigned char *__restrict__ mask,
+                      uint32_t n_mask, uint32_t inner, uint32_t b_len, float *out) {
+    double sum = 0.0;
+    uint32_t cnt = 0;
+    for (uint32_t m = threadIdx.x; m < n_mask; m += ML_BLOCK) {
+        if (!mask[m]) continue;             // masked-out entries are never read into the sum (NaN / Inf there are dropped)
+        ++cnt;
+        for (uint32_t c = 0; c < inner; ++c) {
+            const size_t i = (size_t)m * inner + c;
+            sum += (double)fabsf(a[i] - b[i % b_len]);
+        }
+    }
+    __shared__ double ssum[ML_BLOCK / 32];
+    __shared__ uint32_t scnt[ML_BLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = sum; scnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        uint32_t n = 0;
+        for (int w = 0; w < ML_BLOCK / 32; ++w) { t += ssum[w]; n += scnt[w]; }
+        const float count = (float)n * (float)inner;
+        out[0] = (float)t / count;          // 0 / 0 = NaN for an empty selection, like the mean of an empty tensor
+        out[1] = count;
+    }
+}
+// ga = g * sign(a - b) / count on the selected entries, 0 elsewhere
+__global__ void masked_l1_mean_backward_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                               const unsigned char *__restrict__ mask, uint32_t n_mask, uint32_t inner,
+                                               uint32_t b_len, const float *__restrict__ out, const float *__restrict__ g,
+                                               float *ga) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_mask * inner) return;
+    float r = 0.f;
+    if (mask[i / inner]) {
+        const float d = a[i] - b[i % b_len];
+        r = g[0] * sgnf(d) / out[1];
+    }
+    ga[i] = r;
+}
+
 }  // namespace nicer
 
 using namespace nicer;
@@ -202,5 +251,26 @@ extern "C" int nicer_slam_loss(const nicer_loss_t *args, double *acc, float *mas
     if (a.grad_theta && a.G > 0) loss_points_kernel<<<div_up(a.G, LP_BLOCK), LP_BLOCK, 0, st>>>(a, acc);
     loss_finalize_kernel<<<1, LF_BLOCK, 0, st>>>(a, acc, maskf, terms);
     NICER_CHECK_LAUNCH("nicer_slam_loss");
+    return 0;
+}
+
+extern "C" int nicer_masked_l1_mean(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask, uint32_t inner,
+                                    uint32_t b_len, float *out, void *stream) {
+    if (!a || !b || !mask || !out) NICER_FAIL(-1, "nicer_masked_l1_mean: NULL pointer");
+    if (inner == 0 || b_len == 0) NICER_FAIL(-1, "nicer_masked_l1_mean: inner and b_len must be > 0");
+    masked_l1_mean_kernel<<<1, ML_BLOCK, 0, (cudaStream_t)stream>>>(a, b, mask, n_mask, inner, b_len, out);
+    NICER_CHECK_LAUNCH("nicer_masked_l1_mean");
+    return 0;
+}
+
+extern "C" int nicer_masked_l1_mean_backward(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask,
+                                             uint32_t inner, uint32_t b_len, const float *out, const float *g, float *ga,
+                                             void *stream) {
+    if (n_mask == 0) return 0;
+    if (!a || !b || !mask || !out || !g || !ga) NICER_FAIL(-1, "nicer_masked_l1_mean_backward: NULL pointer");
+    if (inner == 0 || b_len == 0) NICER_FAIL(-1, "nicer_masked_l1_mean_backward: inner and b_len must be > 0");
+    const size_t n = (size_t)n_mask * inner;
+    masked_l1_mean_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, mask, n_mask, inner, b_len, out, g, ga);
+    NICER_CHECK_LAUNCH("nicer_masked_l1_mean_backward");
     return 0;
 }

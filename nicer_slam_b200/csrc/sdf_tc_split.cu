@@ -1,0 +1,644 @@
+// Tensor-core (tcgen05, sm_100a) SDF network main pass, TWO THREADS PER POINT.
+//
+// Same four kernels, same math, same saved tensors and the same staged operands as sdf_tc_full.cu (A: layers + feature
+// head, B: gradient chain, T: tangent pass, R: reverse pass; plans in sdf_tc_plan.cuh).  What changes is the mapping of
+// the per-point epilogue work: a 128-point tile is served by 256 threads, thread pair (h = 0, 1) of a point sharing its TMEM
+// lane -- warp w and warp w + 4 of a tile address the same lane quarter -- and splitting the 64 accumulator columns in
+// halves [32 h, 32 h + 32).  The 80-column layer-0 operand [32 grid | 39 PE | pad] splits the same way: h = 0 owns the grid
+// part (features, d feat/dx rows, grid-gradient hand-over), h = 1 the x / positional-encoding part.
+//
+// Why: with one thread per point the kernels held 64-wide register arrays (254-255 registers, 8 warps per SM) and ncu
+// showed them waiting on their own instruction / memory latency (long scoreboard 48 %, tensor pipe 6-9 %, issue slots
+// 20-33 % busy; profiles/r01_ncu_sdf_backward_summary.txt).  Half-width arrays fit 128 registers, so a CTA runs
+// 16 warps, every thread has its saved rows loaded and all four accumulator chunks fetched before it starts computing, and
+// the per-tile dependent chain between two MMA groups is half as long.  The few per-point scalars that need both halves
+// (sdf = w_n . a_n, d sdf/dx, dL/dx) cross through a 2 KB shared-memory hand-over, ordered by the tile's named barrier.
+#include "sdf_tc_plan.cuh"
+
+namespace nicer {
+
+constexpr int TCS_THREADS = 512;
+
+struct TcsShared {
+    uint64_t bars[2];
+    uint32_t tmem_slot;
+    float xch[2][128][4];     // [tile][point][..]: partial results handed from one column half to the other
+};
+
+__device__ __forceinline__ void tile_sync2(const Tile &t) { asm volatile("bar.sync %0, 256;" ::"r"(t.id) : "memory"); }
+
+// as gemm_issue (tc_tile.cuh) for a 256-thread tile
+__device__ __forceinline__ void gemm_issue2(Tile &t, uint32_t whi, uint32_t wlo, int K, int N) {
+    tc::wait_st();
+    tc::fence_before_sync();
+    tile_sync2(t);
+    if (t.leader) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)N);
+        const uint32_t chunk = (uint32_t)N * 16u;
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const uint64_t bhi = tc::smem_desc(whi + (uint32_t)ks * 2u * chunk, chunk, 128u);
+            const uint64_t blo = tc::smem_desc(wlo + (uint32_t)ks * 2u * chunk, chunk, 128u);
+            const uint32_t ahi = t.tmem + ks * 8, alo = t.tmem + t.alo + ks * 8;
+            tc::mma_tf32_ts(t.tmem + t.dcol, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
+            tc::mma_tf32_ts(t.tmem + t.dcol, alo, bhi, idesc, 1u);
+            tc::mma_tf32_ts(t.tmem + t.dcol, ahi, blo, idesc, 1u);
+        }
+        tc::mma_commit(t.bar);
+    }
+}
+__device__ __forceinline__ void mat_issue2(Tile &t, const TcfPlan &pl, int i, float *smem) {
+    gemm_issue2(t, tc::smem_u32(smem + pl.m[i].hi), tc::smem_u32(smem + pl.m[i].lo), pl.m[i].K, pl.m[i].rows);
+}
+__device__ __forceinline__ void mat_gemm2(Tile &t, const TcfPlan &pl, int i, float *smem) {
+    mat_issue2(t, pl, i, smem);
+    gemm_wait(t);
+}
+
+// barriers + TMEM of a two-tile, 512-thread CTA; returns the calling thread's tile. Call after the operands are staged.
+__device__ __forceinline__ Tile tile_setup2(TcsShared &sh) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { tc::mbar_init(&sh.bars[0], 1); tc::mbar_init(&sh.bars[1], 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc(&sh.tmem_slot, TCF_TMEM);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    Tile t;
+    const int tile = tid >> 8;
+    t.tmem = sh.tmem_slot + (uint32_t)tile * TCF_TILE_COLS;
+    t.lane_base = t.tmem + ((uint32_t)((warp & 3) * 32) << 16);     // warps w and w + 4 of a tile: same lane quarter
+    t.bar = &sh.bars[tile];
+    t.parity = 0;
+    t.id = 1 + tile;
+    t.leader = (tid & 255) == 0;
+    t.alo = TCF_ALO;
+    t.dcol = TCF_D;
+    return t;
+}
+
+__device__ __forceinline__ void tile_teardown2(TcsShared &sh) {
+    tc::fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
+}
+
+// 32 values of one saved layer row-block (this thread's column half) for this point, issued together
+__device__ __forceinline__ void load32(const float *__restrict__ base, size_t row0, size_t Ps, uint32_t p, float v[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __ldg(base + (row0 + j) * Ps + p);
+}
+__device__ __forceinline__ void load32_rw(const float *base, size_t row0, size_t Ps, uint32_t p, float v[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = base[(row0 + j) * Ps + p];
+}
+// this thread's four accumulator chunks (32 columns starting at 32 h)
+__device__ __forceinline__ void ld_half(const Tile &t, int c0, float v[32]) {
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) ld_d8(t, c0 + c8, &v[c8 * 8]);
+    tc::wait_ld();
+}
+__device__ __forceinline__ void st_half(const Tile &t, int c0, const float v[32]) {
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) st_a8(t, c0 + c8, &v[c8 * 8]);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel A
+template <int C>
+__global__ void __launch_bounds__(TCS_THREADS, 1)
+sdf_forward_tcs_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
+                         uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z, float *DYDX, float *H0) {
+    // H0 != NULL: its grid rows (and DYDX) were already written by grid_encode_kernel; this kernel adds the x / PE rows
+    extern __shared__ __align__(16) float smem[];
+    __shared__ TcsShared sh;
+    LevelInfo *lv;
+    tcf_stage_all(net, ls, pl, smem, lv);
+    Tile t = tile_setup2(sh);
+    const int n = (int)net.n_hidden, L = (int)net.grid.L;
+    const int h = (threadIdx.x >> 7) & 1, c0 = 4 * h, tile = threadIdx.x >> 8, lane = threadIdx.x & 127;
+    const size_t Ps = P;
+    const float df = net.grid.divide_factor;
+    const bool accumulate = (flags & NICER_SDF_ACCUMULATE) != 0;
+    const bool want_feat = (flags & NICER_SDF_NO_FEAT) == 0;
+    const float *wl = smem + pl.wl_sdf;
+    const float bl_sdf = net.b[n][0];
+
+    const uint32_t tiles = (P + 127u) / 128u;
+    for (uint32_t tt = blockIdx.x * 2 + tile; tt < ((tiles + 1u) & ~1u); tt += gridDim.x * 2) {
+        uint32_t p = tt * 128u + lane;
+        const bool valid = p < P;
+        if (!valid) p = P - 1;
+        // ---------------- network input -> A   (columns: [32 grid | 39 PE | pad])
+        if (h == 1) {
+            const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+            float pe[48];
+            pe[0] = x[0]; pe[1] = x[1]; pe[2] = x[2];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                float sc[12];
+                pe_sincos<6>(x[d], sc);
+#pragma unroll
+                for (int f = 0; f < 6; ++f) { pe[3 + 6 * f + d] = sc[2 * f]; pe[3 + 6 * f + 3 + d] = sc[2 * f + 1]; }
+            }
+#pragma unroll
+            for (int k = 39; k < 48; ++k) pe[k] = 0.f;
+#pragma unroll
+            for (int c8 = 0; c8 < 6; ++c8) st_a8(t, 4 + c8, &pe[c8 * 8]);      // columns 32..79
+            if (H0 && valid) {
+#pragma unroll
+                for (int k = 0; k < 39; ++k) H0[(size_t)k * Ps + p] = pe[k];
+            }
+        } else if (H0) {
+            // grid features were gathered by grid_encode_kernel into the grid rows of H0 (and DYDX): coalesced reads
+            float gf[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) gf[k] = (k < L * C) ? __ldg(H0 + (size_t)(39 + k) * Ps + p) : 0.f;
+            st_half(t, 0, gf);
+        } else {
+            const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+            float u[3];
+            to_unit(x, df, u);
+#pragma unroll
+            for (int l = 0; l < 32 / C; ++l) {
+                float feat[C], dfeat[3][C];
+                if (l < L) {
+                    encode_level<C, true>(net.grid.table, lv[l], u, feat, dfeat);
+                    if (valid) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+#pragma unroll
+                            for (int c = 0; c < C; ++c) DYDX[((size_t)(l * 3 + d) * C + c) * Ps + p] = dfeat[d][c];
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) feat[c] = 0.f;
+                }
+                st_a_small<C>(t, l * C, feat);
+            }
+        }
+        // ---------------- hidden layers
+        float s_part = (h == 0) ? bl_sdf : 0.f;
+        for (int l = 0; l < n; ++l) {
+            mat_gemm2(t, pl, l, smem);
+            const float *bias = smem + pl.bias[l] + c0 * 8;
+            const bool last = (l == n - 1);
+            float v[32];
+            ld_half(t, c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float z = v[i] + bias[i];
+                if (valid) Z[((size_t)l * NICER_W + c0 * 8 + i) * Ps + p] = z;
+                const SpEval sp = sp_eval(z);
+                v[i] = sp.a;
+                if (last) s_part += wl[c0 * 8 + i] * sp.a;
+            }
+            st_half(t, c0, v);
+        }
+        // ---------------- sdf = b + w_n . a_n: upper half of the dot product handed over through shared memory
+        if (h == 1) sh.xch[tile][lane][0] = s_part;
+        if (want_feat) mat_issue2(t, pl, n, smem); else tile_sync2(t);       // both contain the tile barrier
+        if (h == 0 && valid) {
+            const float s_out = s_part + sh.xch[tile][lane][0];
+            if (accumulate) sdf[p] += s_out; else sdf[p] = s_out;
+        }
+        // ---------------- feature head
+        if (want_feat) {
+            gemm_wait(t);
+            const float *bias = smem + pl.bias[n] + c0 * 8;
+            float v[32];
+            ld_half(t, c0, v);
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float *dst = feat_fm + (size_t)(c0 * 8 + i) * Ps + p;
+                    const float f = v[i] + bias[i];
+                    if (accumulate) *dst += f; else *dst = f;
+                }
+            }
+        }
+    }
+    tile_teardown2(sh);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel B
+// gradient chain  q_n = W_n[0,:] * sp'(z_n),  r_{l-1} = W_{l-1}^T q_l,  q_l = r_l * sp'(z_l),  g = J^T r_0
+template <int C>
+__global__ void __launch_bounds__(TCS_THREADS, 1)
+sdf_forward_tcs_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
+                         uint32_t P, uint32_t flags, float *grad, const float *Z, float *R, const float *DYDX) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ TcsShared sh;
+    LevelInfo *lv;
+    tcf_stage_all(net, ls, pl, smem, lv);
+    Tile t = tile_setup2(sh);
+    const int n = (int)net.n_hidden, L = (int)net.grid.L;
+    const int h = (threadIdx.x >> 7) & 1, c0 = 4 * h, tile = threadIdx.x >> 8, lane = threadIdx.x & 127;
+    const size_t Ps = P;
+    const float df = net.grid.divide_factor;
+    const bool accumulate = (flags & NICER_SDF_ACCUMULATE) != 0;
+    const float *wl = smem + pl.wl_sdf + c0 * 8;
+    const uint32_t tiles = (P + 127u) / 128u;
+    for (uint32_t tt = blockIdx.x * 2 + tile; tt < ((tiles + 1u) & ~1u); tt += gridDim.x * 2) {
+        uint32_t p = tt * 128u + lane;
+        const bool valid = p < P;
+        if (!valid) p = P - 1;
+        {   // q_n -> A
+            float v[32];
+            load32(Z, (size_t)(n - 1) * NICER_W + c0 * 8, Ps, p, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = wl[i] * dsoftplus100(v[i]);
+            st_half(t, c0, v);
+        }
+        for (int l = n - 1; l >= 1; --l) {
+            mat_issue2(t, pl, l, smem);          // r_l = W_l^T q_{l+1}
+            float zv[32], v[32];
+            load32(Z, (size_t)(l - 1) * NICER_W + c0 * 8, Ps, p, zv);
+            gemm_wait(t);
+            ld_half(t, c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (valid) R[((size_t)(l - 1) * NICER_W + c0 * 8 + i) * Ps + p] = v[i];
+                v[i] *= dsoftplus100(zv[i]);
+            }
+            st_half(t, c0, v);
+        }
+        mat_issue2(t, pl, 0, smem);              // r_0 = W_0^T q_1   (80 columns: [32 grid | 39 PE | pad])
+        if (h == 1) {
+            const float x[3] = {__ldg(X + 3 * (size_t)p), __ldg(X + 3 * (size_t)p + 1), __ldg(X + 3 * (size_t)p + 2)};
+            gemm_wait(t);
+            float rp[40];   // PE part: columns 32..71
+#pragma unroll
+            for (int c8 = 0; c8 < 5; ++c8) ld_d8(t, 4 + c8, &rp[c8 * 8]);
+            tc::wait_ld();
+            float g[3] = {rp[0], rp[1], rp[2]};
+            float fr = 1.0f;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float s, c;
+                    sincosf(x[d] * fr, &s, &c);
+                    g[d] += fr * (c * rp[3 + 6 * f + d] - s * rp[3 + 6 * f + 3 + d]);
+                }
+                fr *= 2.0f;
+            }
+            tile_sync2(t);                       // grid part of d sdf/dx from the other half
+            if (valid) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float gd = g[d] + sh.xch[tile][lane][d];
+                    if (accumulate) grad[3 * (size_t)p + d] += gd; else grad[3 * (size_t)p + d] = gd;
+                }
+            }
+        } else {
+            float dyv[96];
+#pragma unroll
+            for (int k = 0; k < 96; ++k) dyv[k] = (k < L * 3 * C) ? __ldg(DYDX + (size_t)k * Ps + p) : 0.f;
+            gemm_wait(t);
+            float gu[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                float rh[8];    // grid part: columns 0..31
+                ld_d8(t, c8, rh);
+                tc::wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = c8 * 8 + i;
+                    if (k < L * C) {
+                        const int l = k / C, c = k % C;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) gu[d] += rh[i] * dyv[(l * 3 + d) * C + c];
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) sh.xch[tile][lane][d] = gu[d] / 2.0f / df;
+            tile_sync2(t);
+        }
+    }
+    tile_teardown2(sh);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel T
+// tangent pass: t_0 = J g_bar, u_1 = W_0 t_0, tan_l = u_l * sp'(z_l), u_{l+1} = W_l tan_l; writes TAN, QB, AB, ZB, T0
+template <int C>
+__global__ void __launch_bounds__(TCS_THREADS, 1)
+sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
+                          uint32_t P, const float *Z, const float *R, const float *DYDX, const float *g_grad, float *ZB,
+                          float *QB, float *AB, float *TAN, float *T0) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ TcsShared sh;
+    LevelInfo *lv;
+    tcf_stage_all(net, ls, pl, smem, lv);
+    Tile t = tile_setup2(sh);
+    const int n = (int)net.n_hidden, L = (int)net.grid.L;
+    const int h = (threadIdx.x >> 7) & 1, c0 = 4 * h, tile = threadIdx.x >> 8, lane = threadIdx.x & 127;
+    const size_t Ps = P;
+    const float df = net.grid.divide_factor;
+    const float *wl = smem + pl.wl_sdf + c0 * 8;
+    const uint32_t tiles = (P + 127u) / 128u;
+    for (uint32_t tt = blockIdx.x * 2 + tile; tt < ((tiles + 1u) & ~1u); tt += gridDim.x * 2) {
+        uint32_t p = tt * 128u + lane;
+        const bool valid = p < P;
+        if (!valid) p = P - 1;
+        float gg[3] = {0.f, 0.f, 0.f};
+        if (g_grad) { gg[0] = g_grad[3 * (size_t)p]; gg[1] = g_grad[3 * (size_t)p + 1]; gg[2] = g_grad[3 * (size_t)p + 2]; }
+        if (h == 1) {
+            // ---- t_0: PE part (columns 32..70), rows 0..38 of T0
+            const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+            float tp[48];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                tp[d] = gg[d];
+                if (valid) T0[(size_t)d * Ps + p] = gg[d];
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                float sc[12];
+                pe_sincos<6, true>(x[d], sc);
+                float fr = 1.0f;
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    const int ks = 3 + 6 * f + d, kc = ks + 3;
+                    const float ts = fr * sc[2 * f + 1] * gg[d], tcv = -fr * sc[2 * f] * gg[d];
+                    tp[ks] = ts; tp[kc] = tcv;
+                    if (valid) { T0[(size_t)ks * Ps + p] = ts; T0[(size_t)kc * Ps + p] = tcv; }
+                    fr *= 2.0f;
+                }
+            }
+#pragma unroll
+            for (int k = 39; k < 48; ++k) tp[k] = 0.f;
+#pragma unroll
+            for (int c8 = 0; c8 < 6; ++c8) st_a8(t, 4 + c8, &tp[c8 * 8]);
+        } else {
+            // ---- t_0: grid part (columns 0..31), rows 39.. of T0
+            float ggu[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) ggu[d] = gg[d] / 2.0f / df;
+            float dyv[96];
+#pragma unroll
+            for (int k = 0; k < 96; ++k) dyv[k] = (k < L * 3 * C) ? __ldg(DYDX + (size_t)k * Ps + p) : 0.f;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                float tv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = c8 * 8 + i, l = k / C, c = k % C;
+                    tv[i] = (k < L * C) ? ggu[0] * dyv[(l * 3 + 0) * C + c] + ggu[1] * dyv[(l * 3 + 1) * C + c] + ggu[2] * dyv[(l * 3 + 2) * C + c] : 0.f;
+                    if (valid && k < L * C) T0[(size_t)(39 + k) * Ps + p] = tv[i];
+                }
+                st_a8(t, c8, tv);
+            }
+        }
+        mat_issue2(t, pl, 0, smem);   // u_1 = W_0 t_0
+        for (int l = 1; l <= n; ++l) {
+            float zv[32], rv[32], v[32];
+            const size_t row0 = (size_t)(l - 1) * NICER_W + c0 * 8;
+            load32(Z, row0, Ps, p, zv);
+            if (l < n) {
+                load32(R, row0, Ps, p, rv);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) rv[j] = wl[j];
+            }
+            gemm_wait(t);
+            ld_half(t, c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const size_t o = (row0 + i) * Ps + p;
+                const SpEval sp = sp_eval(zv[i]);
+                const float u = v[i];
+                const float tan = u * sp.s1;
+                if (valid) {
+                    TAN[o] = tan;
+                    QB[o] = rv[i] * sp.s1;
+                    AB[o] = sp.a;
+                    ZB[o] = u * rv[i] * sp.s2;
+                }
+                v[i] = tan;
+            }
+            if (l < n) {
+                st_half(t, c0, v);
+                mat_issue2(t, pl, l, smem);   // u_{l+1} = W_l tan_l
+            }
+        }
+    }
+    tile_teardown2(sh);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel R
+// reverse pass.  abar_n = W_n^T [g_sdf, g_feat],  zbar_l = abar_l sp'(z_l) + ZB_l,  abar_{l-1} = W_{l-1}^T zbar_l,
+// hbar_0 = W_0^T zbar_1,  r_0 = W_0^T q_1 (second-order terms); writes zbar_l into ZB, the grid gradients into GY, dL/dx.
+template <int C>
+__global__ void __launch_bounds__(TCS_THREADS, 1)
+sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
+                          uint32_t P, const float *Z, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
+                          const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ TcsShared sh;
+    LevelInfo *lv;
+    tcf_stage_all(net, ls, pl, smem, lv);
+    Tile t = tile_setup2(sh);
+    const int n = (int)net.n_hidden, L = (int)net.grid.L;
+    const int h = (threadIdx.x >> 7) & 1, c0 = 4 * h, tile = threadIdx.x >> 8, lane = threadIdx.x & 127;
+    const size_t Ps = P;
+    const float df = net.grid.divide_factor;
+    const float *wl = smem + pl.wl_sdf + c0 * 8;
+    const uint32_t tiles = (P + 127u) / 128u;
+    for (uint32_t tt = blockIdx.x * 2 + tile; tt < ((tiles + 1u) & ~1u); tt += gridDim.x * 2) {
+        uint32_t p = tt * 128u + lane;
+        const bool valid = p < P;
+        if (!valid) p = P - 1;
+        const float gs = g_sdf ? g_sdf[p] : 0.f;
+        // ---- A = g_feat -> abar_n' = (W_n[1:])^T g_feat
+        {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = g_feat_fm ? g_feat_fm[(size_t)(c0 * 8 + i) * Ps + p] : 0.f;
+            st_half(t, c0, v);
+        }
+        mat_issue2(t, pl, n, smem);
+        for (int l = n; l >= 1; --l) {
+            float zv[32], cv[32], v[32];
+            const size_t row0 = (size_t)(l - 1) * NICER_W + c0 * 8;
+            load32(Z, row0, Ps, p, zv);
+            load32_rw(ZB, row0, Ps, p, cv);
+            gemm_wait(t);
+            ld_half(t, c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float abar = (l == n) ? v[i] + wl[i] * gs : v[i];
+                const float zb = abar * dsoftplus100(zv[i]) + cv[i];
+                if (valid) ZB[(row0 + i) * Ps + p] = zb;
+                v[i] = zb;
+            }
+            st_half(t, c0, v);
+            mat_issue2(t, pl, l - 1, smem);   // abar_{l-1} = W_{l-1}^T zbar_l   (l == 1: hbar_0, 80 columns)
+        }
+        float q1[32];
+        load32(QB, (size_t)c0 * 8, Ps, p, q1);
+        if (h == 1) {
+            // ---- PE part of hbar_0 and of r_0 -> dL/dx
+            const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
+            float gg[3] = {0.f, 0.f, 0.f};
+            if (g_grad) { gg[0] = g_grad[3 * (size_t)p]; gg[1] = g_grad[3 * (size_t)p + 1]; gg[2] = g_grad[3 * (size_t)p + 2]; }
+            gemm_wait(t);
+            float xb[3];
+            float pesc[36];     // sin/cos of the PE, reused for the second-order term below
+            {
+                float hp[40];
+#pragma unroll
+                for (int c8 = 0; c8 < 5; ++c8) ld_d8(t, 4 + c8, &hp[c8 * 8]);
+                tc::wait_ld();
+                xb[0] = hp[0]; xb[1] = hp[1]; xb[2] = hp[2];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    pe_sincos<6, true>(x[d], &pesc[12 * d]);
+                    float fr = 1.0f;
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) {
+                        xb[d] += fr * (pesc[12 * d + 2 * f + 1] * hp[3 + 6 * f + d] - pesc[12 * d + 2 * f] * hp[3 + 6 * f + 3 + d]);
+                        fr *= 2.0f;
+                    }
+                }
+            }
+            st_half(t, c0, q1);
+            mat_gemm2(t, pl, 0, smem);          // r_0 = W_0^T q_1
+            {
+                float rp[40];
+#pragma unroll
+                for (int c8 = 0; c8 < 5; ++c8) ld_d8(t, 4 + c8, &rp[c8 * 8]);
+                tc::wait_ld();
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float fr = 1.0f;
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) {
+                        xb[d] += gg[d] * (fr * fr) * (-pesc[12 * d + 2 * f] * rp[3 + 6 * f + d] - pesc[12 * d + 2 * f + 1] * rp[3 + 6 * f + 3 + d]);
+                        fr *= 2.0f;
+                    }
+                }
+            }
+            tile_sync2(t);                      // grid part of dL/dx from the other half
+            if (grad_x && valid) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) grad_x[3 * (size_t)p + d] += xb[d] + sh.xch[tile][lane][d];
+            }
+        } else {
+            // ---- grid part of hbar_0 (first-order grid gradient, dL/dx through d feat/dx) and of r_0 (second-order)
+            float dyv[96];
+#pragma unroll
+            for (int k = 0; k < 96; ++k) dyv[k] = (k < L * 3 * C) ? __ldg(DYDX + (size_t)k * Ps + p) : 0.f;
+            gemm_wait(t);
+            float xu[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int l = 0; l < 32 / C; ++l) {
+                if (l < L) {
+                    float gy1[C];
+                    ld_d_small<C>(t, l * C, gy1);
+                    tc::wait_ld();
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) xu[d] += gy1[c] * dyv[(l * 3 + d) * C + c];
+                        if (valid) GY[(size_t)(l * C + c) * Ps + p] = gy1[c];
+                    }
+                }
+            }
+            st_half(t, c0, q1);
+            mat_gemm2(t, pl, 0, smem);          // r_0 = W_0^T q_1
+#pragma unroll
+            for (int l = 0; l < 32 / C; ++l) {
+                if (l < L) {
+                    float gy2[C];
+                    ld_d_small<C>(t, l * C, gy2);
+                    tc::wait_ld();
+                    if (valid) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) GY[(size_t)((L + l) * C + c) * Ps + p] = gy2[c];
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) sh.xch[tile][lane][d] = xu[d] / 2.0f / df;
+            tile_sync2(t);
+        }
+    }
+    tile_teardown2(sh);
+}
+
+int launch_grid_encode(const nicer_grid_t *g, const float *x, uint32_t P, float *F, float *DYDX, cudaStream_t st);
+int launch_grid_scatter(const nicer_grid_t *g, const float *x, uint32_t P, const float *GY1, const float *GY2,
+                        const float *g_grad, float *grad_table, cudaStream_t st);
+
+// NICER_TC_SPLIT=0 selects the one-thread-per-point kernels of sdf_tc_full.cu (kept for comparison)
+bool tc_split_enabled() {
+    static const bool on = [] { const char *e = getenv("NICER_TC_SPLIT"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+int launch_sdf_forward_tcs(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
+                           float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st) {
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
+    const uint32_t pairs = div_up(div_up(P, 128), 2);
+    const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
+    const TcfPlan pa = plan_a(net), pb = plan_b(net);
+    const size_t smem_a = (size_t)pa.total_floats * sizeof(float), smem_b = (size_t)pb.total_floats * sizeof(float);
+    if (H0) {       // gathers at full occupancy, into the grid rows of the saved network input
+        if (int e = launch_grid_encode(&net->grid, x, P, H0 + (size_t)39 * P, DYDX, st)) return e;
+    }
+#define LAUNCH(CC)                                                                                                      \
+    do {                                                                                                                \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tcs_a_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a), \
+                   "nicer_sdf_forward(tcs A)");                                                                         \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tcs_b_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), \
+                   "nicer_sdf_forward(tcs B)");                                                                         \
+        sdf_forward_tcs_a_kernel<CC><<<grid, TCS_THREADS, smem_a, st>>>(*net, ls, pa, x, P, flags, sdf, feat_fm, Z, DYDX, H0); \
+        sdf_forward_tcs_b_kernel<CC><<<grid, TCS_THREADS, smem_b, st>>>(*net, ls, pb, x, P, flags, grad, Z, R, DYDX);       \
+    } while (0)
+    switch (net->grid.C) {
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        default: LAUNCH(8); break;
+    }
+#undef LAUNCH
+    NICER_CHECK_LAUNCH("nicer_sdf_forward(tcs)");
+    return 0;
+}
+
+int launch_sdf_backward_tcs(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
+                            const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
+                            float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, cudaStream_t st,
+                            cudaStream_t scatter_st) {
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
+    const uint32_t pairs = div_up(div_up(P, 128), 2);
+    const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
+    const TcfPlan pt = plan_t(net), pr = plan_r(net);
+    const size_t smem_t = (size_t)pt.total_floats * sizeof(float), smem_r = (size_t)pr.total_floats * sizeof(float);
+#define LAUNCH(CC)                                                                                                       \
+    do {                                                                                                                 \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_backward_tcs_t_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t), \
+                   "nicer_sdf_backward(tcs T)");                                                                         \
+        NICER_CUDA(cudaFuncSetAttribute(sdf_backward_tcs_r_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r), \
+                   "nicer_sdf_backward(tcs R)");                                                                         \
+        sdf_backward_tcs_t_kernel<CC><<<grid, TCS_THREADS, smem_t, st>>>(*net, ls, pt, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0); \
+        sdf_backward_tcs_r_kernel<CC><<<grid, TCS_THREADS, smem_r, st>>>(*net, ls, pr, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, \
+                                                                         ZB, QB, GY);                                    \
+    } while (0)
+    switch (net->grid.C) {
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        default: LAUNCH(8); break;
+    }
+#undef LAUNCH
+    NICER_CHECK_LAUNCH("nicer_sdf_backward(tcs)");
+    if (scatter_st && scatter_st != st) {
+        if (int e = stream_fork(st, scatter_st)) return e;
+    } else {
+        scatter_st = st;
+    }
+    return launch_grid_scatter(&net->grid, x, P, GY, g_grad ? GY + (size_t)net->grid.L * net->grid.C * P : nullptr, g_grad,
+                               grad_table, scatter_st);
+}
+
+}  // namespace nicer

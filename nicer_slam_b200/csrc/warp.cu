@@ -110,6 +110,27 @@ warp_sample_backward_kernel(const float *__restrict__ depth, const float *__rest
         if (sl[k] != 0.f) atomicAdd(&g_loc[k], sl[k]);
 }
 
+// Ground-truth colour / depth of the patch pixels in their own frame (network.py:226-246): in-image test, integer pixel
+// (truncated, clamped), 1 where the pixel is outside the image.  uvp [B*M,2], img [B,H,W,3], dep [B,H,W]
+__global__ void warp_gt_kernel(const float *__restrict__ uvp, const float *__restrict__ img, const float *__restrict__ dep, uint32_t B,
+                               uint32_t M, uint32_t H, uint32_t W, float *gt_rgb, float *gt_depth, uint8_t *inside) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * M) return;
+    const uint32_t b = e / M;
+    const float u = uvp[2 * (size_t)e], v = uvp[2 * (size_t)e + 1];
+    const bool in = (0.f <= u) && (0.f <= v) && (u < (float)W) && (v < (float)H);
+    float r[3] = {1.0f, 1.0f, 1.0f}, d = 1.0f;
+    if (in) {
+        const uint32_t ui = min((uint32_t)u, W - 1), vi = min((uint32_t)v, H - 1);
+        const size_t px = ((size_t)b * H + vi) * W + ui;
+        r[0] = img[3 * px]; r[1] = img[3 * px + 1]; r[2] = img[3 * px + 2];
+        d = dep[px];
+    }
+    gt_rgb[3 * (size_t)e] = r[0]; gt_rgb[3 * (size_t)e + 1] = r[1]; gt_rgb[3 * (size_t)e + 2] = r[2];
+    gt_depth[e] = d;
+    inside[e] = in ? 1 : 0;
+}
+
 }  // namespace nicer
 
 using namespace nicer;
@@ -137,5 +158,14 @@ extern "C" int nicer_warp_sample_backward(const float *depth, const float *dirs,
     warp_sample_backward_kernel<<<div_up(B * N * pp, WP_BLOCK), WP_BLOCK, 15 * B * sizeof(float), (cudaStream_t)stream>>>(
         depth, dirs, loc, w2c, K, img, B, N, pp, H, W, g_sampled, g_depth, g_dirs, g_loc, g_w2c);
     NICER_CHECK_LAUNCH("nicer_warp_sample_backward");
+    return 0;
+}
+
+extern "C" int nicer_warp_gt(const float *uvp, const float *img, const float *dep, uint32_t B, uint32_t M, uint32_t H, uint32_t W,
+                             float *gt_rgb, float *gt_depth, uint8_t *inside, void *stream) {
+    if (B == 0 || M == 0) return 0;
+    if (!uvp || !img || !dep || !gt_rgb || !gt_depth || !inside) NICER_FAIL(-1, "nicer_warp_gt: NULL pointer");
+    warp_gt_kernel<<<div_up(B * M, 256), 256, 0, (cudaStream_t)stream>>>(uvp, img, dep, B, M, H, W, gt_rgb, gt_depth, inside);
+    NICER_CHECK_LAUNCH("nicer_warp_gt");
     return 0;
 }

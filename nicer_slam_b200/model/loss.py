@@ -14,12 +14,21 @@ from ..utils.MiDaS import ScaleAndShiftInvariantLoss
 
 
 def _masked_mean(values, mask):
-    """mean of values[mask] (NaN for an empty selection, like torch's mean of an empty tensor)."""
-    m = mask.to(values.dtype)
+    """mean of values[mask] (NaN for an empty selection, like torch's mean of an empty tensor).  Masked-out entries are
+    replaced before the sum, so a NaN / Inf there does not reach the result (the reference drops them by indexing)."""
+    m = mask.bool()
     while m.dim() < values.dim():
         m = m.unsqueeze(-1)
     m = m.expand_as(values)
-    return (values * m).sum() / m.sum()
+    return torch.where(m, values, torch.zeros_like(values)).sum() / m.sum()
+
+
+def _masked_l1(a, b, mask):
+    """torch.abs(a[mask] - b[mask]).mean() -- fused kernel for fp32 tensors, elementwise otherwise."""
+    from .. import ops
+    if a.dtype == torch.float32 and b.dtype == torch.float32:
+        return ops.masked_l1_mean(a, b, mask)
+    return _masked_mean(torch.abs(a - b), mask)
 
 
 class SLAMLoss(nn.Module):
@@ -75,7 +84,7 @@ class SLAMLoss(nn.Module):
             return 0.0
         m = ground_truth["flow_mask"].to(model_outputs["flow"].device)
         tgt = ground_truth["flow"].to(model_outputs["flow"].device)
-        return _masked_mean(torch.abs(model_outputs["flow"] - tgt), m)
+        return _masked_l1(model_outputs["flow"], tgt, m)
 
     def forward(self, model_outputs, ground_truth, keyframe_list=None, frame_idx=0, stage="coarse"):
         if isinstance(self.rgb_loss, nn.L1Loss) and model_outputs["rgb_values"].dtype == torch.float32:
@@ -126,7 +135,7 @@ class SLAMLoss(nn.Module):
         if ("warp_output" in model_outputs) and self.warp_loss_weight > 0 and stage == "fine" and frame_idx != 0:
             for patchsize, (gt_rgbs, sampled, mask, _ray_mask) in model_outputs["warp_output"].items():
                 if patchsize == 1 or self.warp_loss_type == "l1":
-                    warp_loss = warp_loss + _masked_mean(torch.abs(sampled - gt_rgbs), mask)
+                    warp_loss = warp_loss + _masked_l1(sampled, gt_rgbs, mask)
                 else:
                     raise NotImplementedError("Strange patch loss type")
         flow_loss = self.get_flow_loss(model_outputs, ground_truth, keyframe_list) if self.flow_weight > 0.0 else 0.0
@@ -160,7 +169,7 @@ class SLAMLoss(nn.Module):
         if ("warp_output" in model_outputs) and self.warp_loss_weight > 0 and stage == "fine" and frame_idx != 0:
             for patchsize, (gt_rgbs, sampled, mask, _ray_mask) in model_outputs["warp_output"].items():
                 if patchsize == 1 or self.warp_loss_type == "l1":
-                    warp_loss = warp_loss + _masked_mean(torch.abs(sampled - gt_rgbs), mask)
+                    warp_loss = warp_loss + _masked_l1(sampled, gt_rgbs, mask)
                 else:
                     raise NotImplementedError("Strange patch loss type")
 

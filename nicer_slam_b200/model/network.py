@@ -152,14 +152,16 @@ class SLAMNetwork(nn.Module):
         rendered_depth = depth_values.unsqueeze(2)
 
         output = {}
+        want_warp = self.use_warp_loss and ("vis" not in mode) and ("tracking" not in mode)
+        # world-to-camera matrices of every frame, once (the reference inverts pose[idjj] and pose separately)
+        w2c_all = ops.inv4x4(pose) if ("edges" in ground_truth or want_warp) else None
         if "edges" in ground_truth:   # optical-flow projection i -> j (network.py:153-165): one kernel per direction
             idii, idjj, _, _ = ground_truth["edges"]
-            w2c = torch.linalg.inv_ex(pose[idjj])[0]     # inv_ex: no host-side error check (CUDA-graph safe)
             output["flow"] = ops.FlowProjectFn.apply(depth_values.reshape(-1), ray_dirs, cam_loc.reshape(bs, num_pixels, 3)[:, 0],
-                                                     w2c, intrinsics[idjj], uv, idii)
+                                                     w2c_all[idjj], intrinsics[idjj], uv, idii)
 
-        if self.use_warp_loss and ("vis" not in mode) and ("tracking" not in mode):
-            output["warp_output"] = self._warp(uv, pose, intrinsics, rendered_depth, ground_truth, batch_size)
+        if want_warp:
+            output["warp_output"] = self._warp(uv, pose, intrinsics, rendered_depth, ground_truth, batch_size, w2c_all)
 
         depth_values = depth_scale * depth_values.reshape(bs, -1, 1)
         if self.white_bkgd:
@@ -198,14 +200,13 @@ class SLAMNetwork(nn.Module):
         return output
 
     # ------------------------------------------------------------------------------------------------
-    def _warp(self, uv, pose, intrinsics, rendered_depth, ground_truth, bs):
+    def _warp(self, uv, pose, intrinsics, rendered_depth, ground_truth, bs, w2c):
         """Photometric warping of every frame's pixels (lifted with the rendered depth) into all frames of the batch
         (network.py:167-279).  Returns {patchsize: (gt_rgb, sampled_rgb, mask, ray_level_depth_mask)}."""
         H, W = self.H, self.W
         full_rgb = ground_truth["full_rgb"].reshape(bs, H, W, 3)
         full_depth = ground_truth["full_depth"].reshape(bs, H, W, 1)
         depth = rendered_depth.reshape(bs, -1, 1, 1)
-        w2c = torch.linalg.inv_ex(pose)[0]
         K3 = intrinsics[:, :3, :3]
         out = {}
         for ps in self.patchsizes:
@@ -214,15 +215,11 @@ class SLAMNetwork(nn.Module):
             dirs_p, loc_p = rend_util.get_camera_params(uv_patch, pose, intrinsics)
             # lift with the rendered depth, project into every frame, bilinear lookup, in-image / in-front mask: one kernel
             sampled, s_mask = ops.WarpSampleFn.apply(depth.reshape(bs, -1), dirs_p, loc_p, w2c, intrinsics, full_rgb, pp)
-            # ground-truth colour / depth of the patch pixels in their own frame (1 where outside the image)
-            u, v = uv_patch[..., 0], uv_patch[..., 1]
-            inside = (0 <= u) & (0 <= v) & (u < W) & (v < H)
-            ui, vi = u.long().clamp(0, W - 1), v.long().clamp(0, H - 1)
-            bi = torch.arange(bs, device=uv.device)[:, None].expand_as(ui)
-            gt_rgb = torch.where(inside[..., None], full_rgb[bi, vi, ui], torch.ones_like(full_rgb[bi, vi, ui]))
-            gt_depth = torch.where(inside[..., None], full_depth[bi, vi, ui], torch.ones_like(full_depth[bi, vi, ui]))
-            g_mask = inside.unsqueeze(0).repeat(bs, 1, 1).reshape(bs, bs, -1, pp)
-            gt_rgbs = gt_rgb.reshape(1, bs, -1, pp, 3).repeat(bs, 1, 1, 1, 1)
+            # ground-truth colour / depth of the patch pixels in their own frame (1 where outside the image): one kernel;
+            # the target is the same for every target frame (the reference materialises bs copies)
+            gt_rgb, gt_depth, inside = ops.warp_gt(uv_patch, full_rgb, full_depth)
+            g_mask = inside.reshape(1, bs, -1, pp).expand(bs, bs, -1, pp)
+            gt_rgbs = gt_rgb.reshape(1, bs, -1, pp, 3).expand(bs, bs, -1, pp, 3)
             total = g_mask & s_mask
             ray_level = None
             if ps > 1:

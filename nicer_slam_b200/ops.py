@@ -625,6 +625,31 @@ class PoseFromCam7Fn(torch.autograd.Function):
         return g
 
 
+class Inv4x4Fn(torch.autograd.Function):
+    """A [B,4,4] -> A^-1: the w2c matrices of the flow / warp blocks (torch.inverse(pose), network.py:157,171), one kernel per
+    direction instead of the ~15 launches of the LU path and its matmul backward."""
+
+    @staticmethod
+    def forward(ctx, A):
+        A = _c(A.detach())
+        Ai = torch.empty_like(A)
+        check(lib().nicer_inv4x4(ptr(A), A.shape[0], ptr(Ai), stream()), "nicer_inv4x4")
+        ctx.save_for_backward(Ai)
+        return Ai
+
+    @staticmethod
+    def backward(ctx, G):
+        (Ai,) = ctx.saved_tensors
+        G = _c(G)
+        GA = torch.empty_like(Ai)
+        check(lib().nicer_inv4x4_backward(ptr(Ai), ptr(G), Ai.shape[0], ptr(GA), stream()), "nicer_inv4x4_backward")
+        return GA
+
+
+def inv4x4(A):
+    return Inv4x4Fn.apply(A.reshape(-1, 4, 4)).reshape(A.shape)
+
+
 class CameraRaysFn(torch.autograd.Function):
     """(uv [B,N,2], pose [B,4,4], K [B,4,4]) -> (ray_dirs [B,N,3], cam_loc [B,3])  (get_camera_params,
     rend_util.py:68-93).  Differentiable w.r.t. the pose only, like the reference's use of it."""
@@ -775,6 +800,64 @@ class WarpSampleFn(torch.autograd.Function):
                                                ptr(g_sampled), ptr(g_depth), ptr(g_dirs), ptr(g_loc), ptr(g_w2c), stream()),
               "nicer_warp_sample_backward")
         return g_depth, g_dirs, g_loc, g_w2c, None, None, None
+
+
+def warp_gt(uv_patch, full_rgb, full_depth):
+    """Ground truth of the warp block (network.py:226-246): uv_patch [B,M,2], full_rgb [B,H,W,3], full_depth [B,H,W,1] ->
+    gt_rgb [B,M,3], gt_depth [B,M,1] (1 outside the image), inside [B,M] bool.  No gradient (ground truth)."""
+    uvp, img, dep = _c(uv_patch.detach().float()), _c(full_rgb.detach().float()), _c(full_depth.detach().float())
+    B, M = uvp.shape[0], uvp.shape[1]
+    H, W = img.shape[1], img.shape[2]
+    gt_rgb = torch.empty(B, M, 3, device=uvp.device)
+    gt_depth = torch.empty(B, M, 1, device=uvp.device)
+    inside = torch.empty(B, M, dtype=torch.bool, device=uvp.device)
+    check(lib().nicer_warp_gt(ptr(uvp), ptr(img), ptr(dep), B, M, H, W, ptr(gt_rgb), ptr(gt_depth),
+                              C.c_void_p(inside.data_ptr()), stream()), "nicer_warp_gt")
+    return gt_rgb, gt_depth, inside
+
+
+class MaskedL1MeanFn(torch.autograd.Function):
+    """mean |a - b| over the selected entries (torch.abs(a[mask] - b[mask]).mean(), loss.py:93-104,145-152): a [..., inner],
+    mask one flag per `inner` values, b either shaped like a or a trailing block of it (leading-dimension broadcast).
+    One kernel per direction; entries that are masked out never enter the sum (NaN / Inf there are dropped, as indexing does)."""
+
+    @staticmethod
+    def forward(ctx, a, b, mask, inner):
+        a_, b_ = _c(a.detach().float()), _c(b.detach().float())
+        m = _c(mask.detach())
+        if m.dtype != torch.bool:
+            m = m != 0
+        n_mask = m.numel()
+        if a_.numel() != n_mask * inner or a_.numel() % b_.numel() != 0:
+            raise ValueError(f"masked_l1_mean: a {tuple(a.shape)}, b {tuple(b.shape)}, mask {tuple(mask.shape)}, inner {inner}")
+        out = torch.empty(2, device=a_.device)
+        check(lib().nicer_masked_l1_mean(ptr(a_), ptr(b_), C.c_void_p(m.data_ptr()), n_mask, inner, b_.numel(), ptr(out),
+                                         stream()), "nicer_masked_l1_mean")
+        ctx.save_for_backward(a_, b_, m, out)
+        ctx.inner, ctx.shape = inner, a.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a_, b_, m, out = ctx.saved_tensors
+        ga = torch.empty_like(a_)
+        g = _c(g.reshape(1).float())
+        check(lib().nicer_masked_l1_mean_backward(ptr(a_), ptr(b_), C.c_void_p(m.data_ptr()), m.numel(), ctx.inner, b_.numel(),
+                                                  ptr(out), ptr(g), ptr(ga), stream()), "nicer_masked_l1_mean_backward")
+        return ga.reshape(ctx.shape), None, None, None
+
+
+def masked_l1_mean(a, b, mask):
+    """a [..., c] or [...]; mask [...] (same leading shape, one flag per trailing c values) or shaped like a; b like a, possibly
+    expanded over leading dimensions (stride 0)."""
+    inner = a.numel() // mask.numel()
+    # an expanded target (the warp ground truth is the same for every target frame) is passed as its un-expanded block
+    lead = 0
+    while lead < b.dim() and b.stride(lead) == 0 and b.shape[lead] > 1:
+        lead += 1
+    if lead:
+        b = b[(0,) * lead]
+    return MaskedL1MeanFn.apply(a, b, mask, inner)
 
 
 # --------------------------------------------------------------------------------------------- flow projection

@@ -455,6 +455,14 @@ extern "C" int nicer_hash_encode_second_backward(const float *grad, const float 
 }
 
 // ---------------------------------------------------------------------------------------------- camera / ray helpers
+extern "C" int nicer_inv4x4(const float *A, uint32_t B, float *Ai, void *) {
+    for (uint32_t b = 0; b < B; ++b) inv4x4(A + 16 * (size_t)b, Ai + 16 * (size_t)b);
+    return 0;
+}
+extern "C" int nicer_inv4x4_backward(const float *Ai, const float *G, uint32_t B, float *GA, void *) {
+    for (uint32_t b = 0; b < B; ++b) inv4x4_backward(Ai + 16 * (size_t)b, G + 16 * (size_t)b, GA + 16 * (size_t)b);
+    return 0;
+}
 extern "C" int nicer_pose_from_cam7(const float *cam7, uint32_t B, float *pose, void *) {
     for (uint32_t b = 0; b < B; ++b) pose_from_cam7(cam7 + 7 * (size_t)b, pose + 16 * (size_t)b);
     return 0;
@@ -672,5 +680,47 @@ extern "C" int nicer_warp_sample_backward(const float *depth, const float *dirs,
         for (int a = 0; a < 3; ++a) { g_dirs[3 * (size_t)e + a] = d * gp[a]; g_loc[3 * i + a] += gp[a]; }
         g_depth[ray] += gp[0] * dir[0] + gp[1] * dir[1] + gp[2] * dir[2];
     }
+    return 0;
+}
+
+extern "C" int nicer_warp_gt(const float *uvp, const float *img, const float *dep, uint32_t B, uint32_t M, uint32_t H, uint32_t W,
+                             float *gt_rgb, float *gt_depth, uint8_t *inside, void *) {
+    for (uint32_t e = 0; e < B * M; ++e) {
+        const uint32_t b = e / M;
+        const float u = uvp[2 * (size_t)e], v = uvp[2 * (size_t)e + 1];
+        const bool in = (0.f <= u) && (0.f <= v) && (u < (float)W) && (v < (float)H);
+        float r[3] = {1.0f, 1.0f, 1.0f}, d = 1.0f;
+        if (in) {
+            const uint32_t ui = std::min((uint32_t)u, W - 1), vi = std::min((uint32_t)v, H - 1);
+            const size_t px = ((size_t)b * H + vi) * W + ui;
+            r[0] = img[3 * px]; r[1] = img[3 * px + 1]; r[2] = img[3 * px + 2];
+            d = dep[px];
+        }
+        for (int c = 0; c < 3; ++c) gt_rgb[3 * (size_t)e + c] = r[c];
+        gt_depth[e] = d;
+        inside[e] = in ? 1 : 0;
+    }
+    return 0;
+}
+
+extern "C" int nicer_masked_l1_mean(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask, uint32_t inner,
+                                    uint32_t b_len, float *out, void *) {
+    double sum = 0.0, cnt = 0.0;
+    for (uint32_t m = 0; m < n_mask; ++m) {
+        if (!mask[m]) continue;
+        cnt += inner;
+        for (uint32_t c = 0; c < inner; ++c) {
+            const size_t i = (size_t)m * inner + c;
+            sum += fabsf(a[i] - b[i % b_len]);
+        }
+    }
+    out[0] = (float)sum / (float)cnt;
+    out[1] = (float)cnt;
+    return 0;
+}
+extern "C" int nicer_masked_l1_mean_backward(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask,
+                                             uint32_t inner, uint32_t b_len, const float *out, const float *g, float *ga, void *) {
+    for (size_t i = 0; i < (size_t)n_mask * inner; ++i)
+        ga[i] = mask[i / inner] ? g[0] * sgnf(a[i] - b[i % b_len]) / out[1] : 0.f;
     return 0;
 }
