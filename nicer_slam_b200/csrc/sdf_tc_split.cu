@@ -251,16 +251,21 @@ sdf_forward_tcs_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
         }
         for (int l = n - 1; l >= 1; --l) {
             mat_issue2(t, pl, l, smem);          // r_l = W_l^T q_{l+1}
-            float zv[32], v[32];
+            float zv[32];
             load32(Z, (size_t)(l - 1) * NICER_W + c0 * 8, Ps, p, zv);
             gemm_wait(t);
-            ld_half(t, c0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (valid) R[((size_t)(l - 1) * NICER_W + c0 * 8 + i) * Ps + p] = v[i];
-                v[i] *= dsoftplus100(zv[i]);
+            for (int c8 = 0; c8 < 4; ++c8) {        // 8 columns at a time: the prefetched rows + one chunk fit 128 registers
+                float v[8];
+                ld_d8(t, c0 + c8, v);
+                tc::wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (valid) R[((size_t)(l - 1) * NICER_W + (c0 + c8) * 8 + i) * Ps + p] = v[i];
+                    v[i] *= dsoftplus100(zv[c8 * 8 + i]);
+                }
+                st_a8(t, c0 + c8, v);
             }
-            st_half(t, c0, v);
         }
         mat_issue2(t, pl, 0, smem);              // r_0 = W_0^T q_1   (80 columns: [32 grid | 39 PE | pad])
         if (h == 1) {
@@ -375,16 +380,19 @@ sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
             float ggu[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) ggu[d] = gg[d] / 2.0f / df;
-            float dyv[96];
-#pragma unroll
-            for (int k = 0; k < 96; ++k) dyv[k] = (k < L * 3 * C) ? __ldg(DYDX + (size_t)k * Ps + p) : 0.f;
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
-                float tv[8];
+                float dy[3][8], tv[8];      // the d feat/dx rows of these 8 features (24 loads in flight per chunk)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int k = c8 * 8 + i, l = k / C, c = k % C;
-                    tv[i] = (k < L * C) ? ggu[0] * dyv[(l * 3 + 0) * C + c] + ggu[1] * dyv[(l * 3 + 1) * C + c] + ggu[2] * dyv[(l * 3 + 2) * C + c] : 0.f;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) dy[d][i] = (k < L * C) ? __ldg(DYDX + (size_t)((l * 3 + d) * C + c) * Ps + p) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = c8 * 8 + i;
+                    tv[i] = (k < L * C) ? ggu[0] * dy[0][i] + ggu[1] * dy[1][i] + ggu[2] * dy[2][i] : 0.f;
                     if (valid && k < L * C) T0[(size_t)(39 + k) * Ps + p] = tv[i];
                 }
                 st_a8(t, c8, tv);
@@ -392,35 +400,45 @@ sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
         }
         mat_issue2(t, pl, 0, smem);   // u_1 = W_0 t_0
         for (int l = 1; l <= n; ++l) {
-            float zv[32], rv[32], v[32];
+            // z_l rows prefetched under the MMAs; the r_l rows follow one 8-column chunk ahead of their use (both sets of 32 plus
+            // the four output streams do not fit 128 registers: ptxas spilled the loaded values, i.e. waited for every load)
+            float zv[32], rc[8];
             const size_t row0 = (size_t)(l - 1) * NICER_W + c0 * 8;
             load32(Z, row0, Ps, p, zv);
-            if (l < n) {
-                load32(R, row0, Ps, p, rv);
-            } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) rv[j] = wl[j];
-            }
+            for (int i = 0; i < 8; ++i) rc[i] = (l < n) ? __ldg(R + (row0 + i) * Ps + p) : wl[i];
             gemm_wait(t);
-            ld_half(t, c0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const size_t o = (row0 + i) * Ps + p;
-                const SpEval sp = sp_eval(zv[i]);
-                const float u = v[i];
-                const float tan = u * sp.s1;
-                if (valid) {
-                    TAN[o] = tan;
-                    QB[o] = rv[i] * sp.s1;
-                    AB[o] = sp.a;
-                    ZB[o] = u * rv[i] * sp.s2;
+            for (int c8 = 0; c8 < 4; ++c8) {
+                float v[8], rn[8];
+                if (c8 < 3) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rn[i] = (l < n) ? __ldg(R + (row0 + (c8 + 1) * 8 + i) * Ps + p) : wl[(c8 + 1) * 8 + i];
                 }
-                v[i] = tan;
+                ld_d8(t, c0 + c8, v);
+                tc::wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = c8 * 8 + i;
+                    const size_t o = (row0 + j) * Ps + p;
+                    const SpEval sp = sp_eval(zv[j]);
+                    const float u = v[i];
+                    const float tan = u * sp.s1;
+                    if (valid) {
+                        TAN[o] = tan;
+                        QB[o] = rc[i] * sp.s1;
+                        AB[o] = sp.a;
+                        ZB[o] = u * rc[i] * sp.s2;
+                    }
+                    v[i] = tan;
+                }
+                if (l < n) st_a8(t, c0 + c8, v);
+                if (c8 < 3) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rc[i] = rn[i];
+                }
             }
-            if (l < n) {
-                st_half(t, c0, v);
-                mat_issue2(t, pl, l, smem);   // u_{l+1} = W_l tan_l
-            }
+            if (l < n) mat_issue2(t, pl, l, smem);   // u_{l+1} = W_l tan_l
         }
     }
     tile_teardown2(sh);
@@ -459,25 +477,31 @@ sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
         }
         mat_issue2(t, pl, n, smem);
         for (int l = n; l >= 1; --l) {
-            float zv[32], cv[32], v[32];
+            float zv[32], cv[32];
             const size_t row0 = (size_t)(l - 1) * NICER_W + c0 * 8;
             load32(Z, row0, Ps, p, zv);
             load32_rw(ZB, row0, Ps, p, cv);
             gemm_wait(t);
-            ld_half(t, c0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float abar = (l == n) ? v[i] + wl[i] * gs : v[i];
-                const float zb = abar * dsoftplus100(zv[i]) + cv[i];
-                if (valid) ZB[(row0 + i) * Ps + p] = zb;
-                v[i] = zb;
+            for (int c8 = 0; c8 < 4; ++c8) {        // 8 columns at a time: the prefetched rows + one chunk fit 128 registers
+                float v[8];
+                ld_d8(t, c0 + c8, v);
+                tc::wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = c8 * 8 + i;
+                    const float abar = (l == n) ? v[i] + wl[j] * gs : v[i];
+                    const float zb = abar * dsoftplus100(zv[j]) + cv[j];
+                    if (valid) ZB[(row0 + j) * Ps + p] = zb;
+                    v[i] = zb;
+                }
+                st_a8(t, c0 + c8, v);
             }
-            st_half(t, c0, v);
             mat_issue2(t, pl, l - 1, smem);   // abar_{l-1} = W_{l-1}^T zbar_l   (l == 1: hbar_0, 80 columns)
         }
-        float q1[32];
-        load32(QB, (size_t)c0 * 8, Ps, p, q1);
         if (h == 1) {
+            float q1[32];
+            load32(QB, (size_t)c0 * 8, Ps, p, q1);
             // ---- PE part of hbar_0 and of r_0 -> dL/dx
             const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
             float gg[3] = {0.f, 0.f, 0.f};
@@ -545,7 +569,11 @@ sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
                     }
                 }
             }
-            st_half(t, c0, q1);
+            {
+                float q1[32];
+                load32(QB, (size_t)c0 * 8, Ps, p, q1);
+                st_half(t, c0, q1);
+            }
             mat_gemm2(t, pl, 0, smem);          // r_0 = W_0^T q_1
 #pragma unroll
             for (int l = 0; l < 32 / C; ++l) {
@@ -567,78 +595,79 @@ sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
     tile_teardown2(sh);
 }
 
-int launch_grid_encode(const nicer_grid_t *g, const float *x, uint32_t P, float *F, float *DYDX, cudaStream_t st);
-int launch_grid_scatter(const nicer_grid_t *g, const float *x, uint32_t P, const float *GY1, const float *GY2,
-                        const float *g_grad, float *grad_table, cudaStream_t st);
-
-// NICER_TC_SPLIT=0 selects the one-thread-per-point kernels of sdf_tc_full.cu (kept for comparison)
-bool tc_split_enabled() {
-    static const bool on = [] { const char *e = getenv("NICER_TC_SPLIT"); return !(e && e[0] == '0'); }();
-    return on;
+// NICER_TC_SPLIT: bit mask of the kernels that run in this two-threads-per-point form (1 = A, 2 = B, 4 = T, 8 = R); the others
+// run as the one-thread-per-point kernels of sdf_tc_full.cu.  Default: see tc_split_mask().
+unsigned tc_split_mask() {
+    static const unsigned m = [] {
+        const char *e = getenv("NICER_TC_SPLIT");
+        return e ? (unsigned)atoi(e) : 15u;
+    }();
+    return m;
 }
 
-int launch_sdf_forward_tcs(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
-                           float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st) {
-    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
-    const uint32_t pairs = div_up(div_up(P, 128), 2);
-    const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
-    const TcfPlan pa = plan_a(net), pb = plan_b(net);
-    const size_t smem_a = (size_t)pa.total_floats * sizeof(float), smem_b = (size_t)pb.total_floats * sizeof(float);
-    if (H0) {       // gathers at full occupancy, into the grid rows of the saved network input
-        if (int e = launch_grid_encode(&net->grid, x, P, H0 + (size_t)39 * P, DYDX, st)) return e;
-    }
-#define LAUNCH(CC)                                                                                                      \
-    do {                                                                                                                \
-        NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tcs_a_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a), \
-                   "nicer_sdf_forward(tcs A)");                                                                         \
-        NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tcs_b_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), \
-                   "nicer_sdf_forward(tcs B)");                                                                         \
-        sdf_forward_tcs_a_kernel<CC><<<grid, TCS_THREADS, smem_a, st>>>(*net, ls, pa, x, P, flags, sdf, feat_fm, Z, DYDX, H0); \
-        sdf_forward_tcs_b_kernel<CC><<<grid, TCS_THREADS, smem_b, st>>>(*net, ls, pb, x, P, flags, grad, Z, R, DYDX);       \
+#define TCS_DISPATCH(KERNEL, SMEM, WHAT, ...)                                                                              \
+    do {                                                                                                                   \
+        switch (net->grid.C) {                                                                                             \
+            case 2:                                                                                                        \
+                NICER_CUDA(cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)), WHAT); \
+                KERNEL<2><<<grid, TCS_THREADS, SMEM, st>>>(__VA_ARGS__);                                                   \
+                break;                                                                                                     \
+            case 4:                                                                                                        \
+                NICER_CUDA(cudaFuncSetAttribute(KERNEL<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)), WHAT); \
+                KERNEL<4><<<grid, TCS_THREADS, SMEM, st>>>(__VA_ARGS__);                                                   \
+                break;                                                                                                     \
+            default:                                                                                                       \
+                NICER_CUDA(cudaFuncSetAttribute(KERNEL<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)), WHAT); \
+                KERNEL<8><<<grid, TCS_THREADS, SMEM, st>>>(__VA_ARGS__);                                                   \
+                break;                                                                                                     \
+        }                                                                                                                  \
+        NICER_CHECK_LAUNCH(WHAT);                                                                                          \
     } while (0)
-    switch (net->grid.C) {
-        case 2: LAUNCH(2); break;
-        case 4: LAUNCH(4); break;
-        default: LAUNCH(8); break;
-    }
-#undef LAUNCH
-    NICER_CHECK_LAUNCH("nicer_sdf_forward(tcs)");
+
+static uint32_t tcs_grid(uint32_t P) {
+    const uint32_t pairs = div_up(div_up(P, 128), 2);
+    return pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
+}
+
+int launch_tcs_a(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z,
+                 float *DYDX, float *H0, cudaStream_t st) {
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
+    const uint32_t grid = tcs_grid(P);
+    const TcfPlan pl = plan_a(net);
+    const size_t smem = (size_t)pl.total_floats * sizeof(float);
+    TCS_DISPATCH(sdf_forward_tcs_a_kernel, smem, "nicer_sdf_forward(tcs A)", *net, ls, pl, x, P, flags, sdf, feat_fm, Z, DYDX, H0);
     return 0;
 }
 
-int launch_sdf_backward_tcs(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
-                            const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
-                            float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, cudaStream_t st,
-                            cudaStream_t scatter_st) {
+int launch_tcs_b(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *grad, const float *Z, float *R,
+                 const float *DYDX, cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
-    const uint32_t pairs = div_up(div_up(P, 128), 2);
-    const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
-    const TcfPlan pt = plan_t(net), pr = plan_r(net);
-    const size_t smem_t = (size_t)pt.total_floats * sizeof(float), smem_r = (size_t)pr.total_floats * sizeof(float);
-#define LAUNCH(CC)                                                                                                       \
-    do {                                                                                                                 \
-        NICER_CUDA(cudaFuncSetAttribute(sdf_backward_tcs_t_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t), \
-                   "nicer_sdf_backward(tcs T)");                                                                         \
-        NICER_CUDA(cudaFuncSetAttribute(sdf_backward_tcs_r_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r), \
-                   "nicer_sdf_backward(tcs R)");                                                                         \
-        sdf_backward_tcs_t_kernel<CC><<<grid, TCS_THREADS, smem_t, st>>>(*net, ls, pt, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0); \
-        sdf_backward_tcs_r_kernel<CC><<<grid, TCS_THREADS, smem_r, st>>>(*net, ls, pr, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, \
-                                                                         ZB, QB, GY);                                    \
-    } while (0)
-    switch (net->grid.C) {
-        case 2: LAUNCH(2); break;
-        case 4: LAUNCH(4); break;
-        default: LAUNCH(8); break;
-    }
-#undef LAUNCH
-    NICER_CHECK_LAUNCH("nicer_sdf_backward(tcs)");
-    if (scatter_st && scatter_st != st) {
-        if (int e = stream_fork(st, scatter_st)) return e;
-    } else {
-        scatter_st = st;
-    }
-    return launch_grid_scatter(&net->grid, x, P, GY, g_grad ? GY + (size_t)net->grid.L * net->grid.C * P : nullptr, g_grad,
-                               grad_table, scatter_st);
+    const uint32_t grid = tcs_grid(P);
+    const TcfPlan pl = plan_b(net);
+    const size_t smem = (size_t)pl.total_floats * sizeof(float);
+    TCS_DISPATCH(sdf_forward_tcs_b_kernel, smem, "nicer_sdf_forward(tcs B)", *net, ls, pl, x, P, flags, grad, Z, R, DYDX);
+    return 0;
+}
+
+int launch_tcs_t(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R, const float *DYDX,
+                 const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st) {
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
+    const uint32_t grid = tcs_grid(P);
+    const TcfPlan pl = plan_t(net);
+    const size_t smem = (size_t)pl.total_floats * sizeof(float);
+    TCS_DISPATCH(sdf_backward_tcs_t_kernel, smem, "nicer_sdf_backward(tcs T)", *net, ls, pl, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0);
+    return 0;
+}
+
+int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *DYDX, const float *g_sdf,
+                 const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY, cudaStream_t st) {
+    const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
+    const uint32_t grid = tcs_grid(P);
+    const TcfPlan pl = plan_r(net);
+    const size_t smem = (size_t)pl.total_floats * sizeof(float);
+    TCS_DISPATCH(sdf_backward_tcs_r_kernel, smem, "nicer_sdf_backward(tcs R)", *net, ls, pl, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad,
+                 grad_x, ZB, QB, GY);
+    return 0;
 }
 
 }  // namespace nicer
