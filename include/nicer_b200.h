@@ -105,6 +105,7 @@ int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, ui
                       float *Z, float *R, float *DYDX, float *H0, void *stream);
 
 /* Backward of (sdf, feat, grad) w.r.t. x, the grid and (through the workspace below) the weights.
+ *   H0 [d_in][P] | NULL       the saved network input (its x / positional-encoding rows are read back instead of recomputed)
  *   g_sdf [P] | NULL, g_feat_fm [64][P] | NULL, g_grad [P,3] | NULL   upstream gradients
  *   grad_x [P,3] | NULL       accumulated (+=)
  *   grad_table [n_entries,C]  accumulated with atomics (first- and second-order terms both land here)
@@ -116,7 +117,7 @@ int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, ui
  *                             kernel to the grid-scatter kernel
  */
 int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P,
-                       const float *Z, const float *R, const float *DYDX,
+                       const float *Z, const float *R, const float *DYDX, const float *H0,
                        const float *g_sdf, const float *g_feat_fm, const float *g_grad,
                        float *grad_x, float *grad_table,
                        float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, void *stream,
@@ -288,9 +289,11 @@ int nicer_warp_gt(const float *uvp, const float *img, const float *dep, uint32_t
 /* nicer_masked_l1_mean: mean |a - b| over the selected entries = torch.abs(a[mask] - b[mask]).mean(), the photometric-warp
  * and optical-flow terms (model/loss.py:93-104,145-152).  a [n_mask*inner], mask [n_mask] (uint8, one per `inner` values),
  * b [b_len] read as b[i % b_len] (b_len = n_mask*inner when not broadcast) -> out[0] = mean, out[1] = number of selected values.
+ * workspace: nicer_masked_l1_mean_workspace() bytes of device memory, 8-byte aligned (per-block partials; no initialisation needed).
  * backward: g [1] = dL/dmean -> ga [n_mask*inner] (written; 0 on unselected entries). */
+size_t nicer_masked_l1_mean_workspace(void);
 int nicer_masked_l1_mean(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask, uint32_t inner,
-                         uint32_t b_len, float *out, void *stream);
+                         uint32_t b_len, void *workspace, float *out, void *stream);
 int nicer_masked_l1_mean_backward(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask, uint32_t inner,
                                   uint32_t b_len, const float *out, const float *g, float *ga, void *stream);
 

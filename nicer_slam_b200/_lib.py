@@ -59,7 +59,7 @@ _SIGS = {
     "nicer_hash_encode_second_backward": [_fp, _fp, _fp, _fp, _u32, _u32, _u32, _u32, C.c_float, _u32, C.c_int, _fp,
                                           _fp, _fp, _fp, _fp],
     "nicer_sdf_forward": [C.POINTER(SdfNetT), _fp, _u32, _u32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
-    "nicer_sdf_backward": [C.POINTER(SdfNetT), _fp, _u32] + [_fp] * 16,
+    "nicer_sdf_backward": [C.POINTER(SdfNetT), _fp, _u32] + [_fp] * 17,
     "nicer_color_forward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32, _fp, _fp, _fp, _fp, _fp],
     "nicer_color_backward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32] + [_fp] * 14,
     "nicer_outer_accum": [_fp, _u32, _u32, _fp, _u32, _u32, _u32, _fp, _u32, _fp, _fp],
@@ -80,7 +80,7 @@ _SIGS = {
     "nicer_slam_loss": [C.POINTER(LossT), _fp, _fp, _fp, _fp],
     "nicer_warp_sample": [_fp] * 6 + [_u32] * 5 + [_fp, _fp, _fp],
     "nicer_warp_gt": [_fp] * 3 + [_u32] * 4 + [_fp] * 4,
-    "nicer_masked_l1_mean": [_fp] * 3 + [_u32] * 3 + [_fp, _fp],
+    "nicer_masked_l1_mean": [_fp] * 3 + [_u32] * 3 + [_fp, _fp, _fp],
     "nicer_masked_l1_mean_backward": [_fp] * 3 + [_u32] * 3 + [_fp] * 4,
     "nicer_warp_sample_backward": [_fp] * 6 + [_u32] * 5 + [_fp] * 6,
     "nicer_pose_from_cam7": [_fp, _u32, _fp, _fp],
@@ -105,6 +105,8 @@ def _bind(h):
         fn.restype = C.c_int
     h.nicer_last_error.restype = C.c_char_p
     h.nicer_version.restype = C.c_int
+    h.nicer_masked_l1_mean_workspace.restype = C.c_size_t
+    h.nicer_masked_l1_mean_workspace.argtypes = []
     return h
 
 
@@ -120,7 +122,7 @@ def lib():
 
 
 def exported_symbols():
-    return sorted(list(_SIGS) + ["nicer_last_error", "nicer_version"])
+    return sorted(list(_SIGS) + ["nicer_last_error", "nicer_version", "nicer_masked_l1_mean_workspace"])
 
 
 def check(rc, what=""):

@@ -189,13 +189,15 @@ loss_finalize_kernel(const nicer_loss_t a, const double *acc, const float *maskf
 // model/loss.py:93-104,145-152 of the reference: torch.abs(x[mask] - y[mask]).mean()).  a, b: [n_mask * inner], mask: one byte
 // per `inner` consecutive values; b may be shorter than a (b_len values, repeated: the warp target is the same for every
 // target frame).  One block: the tensors are a few 100 k values, the reduction order is fixed (deterministic).
-constexpr int ML_BLOCK = 1024;
+constexpr int ML_BLOCK = 256, ML_MAX_BLOCKS = 128;
+// ws: [ML_MAX_BLOCKS] double partial sums, [ML_MAX_BLOCKS] uint32 partial counts, one uint32 ticket (zeroed by the launcher).
+// The last block to finish adds the partials in block order: the result does not depend on the block schedule.
 __global__ void __launch_bounds__(ML_BLOCK)
 masked_l1_mean_kernel(const float *__restrict__ a, const float *__restrict__ b, const unsigned char *__restrict__ mask,
-                      uint32_t n_mask, uint32_t inner, uint32_t b_len, float *out) {
+                      uint32_t n_mask, uint32_t inner, uint32_t b_len, double *ws, float *out) {
     double sum = 0.0;
     uint32_t cnt = 0;
-    for (uint32_t m = threadIdx.x; m < n_mask; m += ML_BLOCK) {
+    for (uint32_t m = blockIdx.x * ML_BLOCK + threadIdx.x; m < n_mask; m += gridDim.x * ML_BLOCK) {
         if (!mask[m]) continue;             // masked-out entries are never read into the sum (NaN / Inf there are dropped)
         ++cnt;
         for (uint32_t c = 0; c < inner; ++c) {
@@ -205,14 +207,27 @@ masked_l1_mean_kernel(const float *__restrict__ a, const float *__restrict__ b, 
     }
     __shared__ double ssum[ML_BLOCK / 32];
     __shared__ uint32_t scnt[ML_BLOCK / 32];
+    __shared__ bool last;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
     if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = sum; scnt[threadIdx.x >> 5] = cnt; }
     __syncthreads();
+    uint32_t *pcnt = reinterpret_cast<uint32_t *>(ws + ML_MAX_BLOCKS), *ticket = pcnt + ML_MAX_BLOCKS;
     if (threadIdx.x == 0) {
         double t = 0.0;
         uint32_t n = 0;
         for (int w = 0; w < ML_BLOCK / 32; ++w) { t += ssum[w]; n += scnt[w]; }
+        ws[blockIdx.x] = t;
+        pcnt[blockIdx.x] = n;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        uint32_t n = 0;
+        for (uint32_t k = 0; k < gridDim.x; ++k) { t += ws[k]; n += pcnt[k]; }
         const float count = (float)n * (float)inner;
         out[0] = (float)t / count;          // 0 / 0 = NaN for an empty selection, like the mean of an empty tensor
         out[1] = count;
@@ -254,11 +269,18 @@ extern "C" int nicer_slam_loss(const nicer_loss_t *args, double *acc, float *mas
     return 0;
 }
 
+extern "C" size_t nicer_masked_l1_mean_workspace(void) { return ML_MAX_BLOCKS * (sizeof(double) + sizeof(uint32_t)) + 16; }
+
 extern "C" int nicer_masked_l1_mean(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask, uint32_t inner,
-                                    uint32_t b_len, float *out, void *stream) {
-    if (!a || !b || !mask || !out) NICER_FAIL(-1, "nicer_masked_l1_mean: NULL pointer");
+                                    uint32_t b_len, void *workspace, float *out, void *stream) {
+    if (!a || !b || !mask || !out || !workspace) NICER_FAIL(-1, "nicer_masked_l1_mean: NULL pointer");
     if (inner == 0 || b_len == 0) NICER_FAIL(-1, "nicer_masked_l1_mean: inner and b_len must be > 0");
-    masked_l1_mean_kernel<<<1, ML_BLOCK, 0, (cudaStream_t)stream>>>(a, b, mask, n_mask, inner, b_len, out);
+    cudaStream_t st = (cudaStream_t)stream;
+    double *ws = static_cast<double *>(workspace);
+    NICER_CUDA(cudaMemsetAsync(reinterpret_cast<uint32_t *>(ws + ML_MAX_BLOCKS) + ML_MAX_BLOCKS, 0, sizeof(uint32_t), st), "nicer_masked_l1_mean");
+    uint32_t blocks = div_up(n_mask, ML_BLOCK * 4);
+    blocks = blocks < 1 ? 1 : (blocks > ML_MAX_BLOCKS ? ML_MAX_BLOCKS : blocks);
+    masked_l1_mean_kernel<<<blocks, ML_BLOCK, 0, st>>>(a, b, mask, n_mask, inner, b_len, ws, out);
     NICER_CHECK_LAUNCH("nicer_masked_l1_mean");
     return 0;
 }

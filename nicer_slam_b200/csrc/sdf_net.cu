@@ -141,7 +141,7 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
                           float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st);
 
 int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
-                           const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
+                           const float *DYDX, const float *H0, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
                            float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, cudaStream_t st,
                            cudaStream_t scatter_st);
 
@@ -194,7 +194,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
 }
 
 extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
-                                  const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
+                                  const float *R, const float *DYDX, const float *H0, const float *g_sdf, const float *g_feat_fm,
                                   const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
                                   float *AB, float *TAN, float *T0, float *GY, void *stream, void *scatter_stream) {
     if (int e = check_sdf_net(net, "nicer_sdf_backward")) return e;
@@ -205,7 +205,7 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_backward: n_hidden > 3 not built");
     if (tc_enabled() && net->multires == 6 && !GY) NICER_FAIL(-1, "nicer_sdf_backward: GY workspace is NULL");
     if (tc_enabled() && net->multires == 6)
-        return launch_sdf_backward_tc(net, x, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB, TAN, T0,
+        return launch_sdf_backward_tc(net, x, P, Z, R, DYDX, H0, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB, TAN, T0,
                                       GY, (cudaStream_t)stream, (cudaStream_t)scatter_stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);

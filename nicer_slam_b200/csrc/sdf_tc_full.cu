@@ -248,11 +248,12 @@ unsigned tc_split_mask();
 int launch_tcs_a(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z,
                  float *DYDX, float *H0, cudaStream_t st);
 int launch_tcs_b(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *grad, const float *Z, float *R,
-                 const float *DYDX, cudaStream_t st);
+                 const float *DYDX, const float *H0, cudaStream_t st);
 int launch_tcs_t(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R, const float *DYDX,
-                 const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st);
-int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *DYDX, const float *g_sdf,
-                 const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY, cudaStream_t st);
+                 const float *H0, const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st);
+int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *DYDX, const float *H0,
+                 const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY,
+                 cudaStream_t st);
 
 int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
                           float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st) {
@@ -265,6 +266,9 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
         if (int e = launch_grid_encode(&net->grid, x, P, H0 + (size_t)39 * P, DYDX, st)) return e;
     }
     const unsigned split = tc_split_mask();
+    // kernel B reads the positional encoding back from the saved input (NICER_PE_RELOAD=0: recomputes it)
+    static const bool pe_reload = [] { const char *e = getenv("NICER_PE_RELOAD"); return !(e && e[0] == '0'); }();
+    const float *pe_h0 = pe_reload ? H0 : nullptr;
 #define LAUNCH(CC)                                                                                                      \
     do {                                                                                                                \
         NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tc_a_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a), \
@@ -273,7 +277,7 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
                    "nicer_sdf_forward(tc B)");                                                                          \
         if (split & 1u) { if (int e = launch_tcs_a(net, x, P, flags, sdf, feat_fm, Z, DYDX, H0, st)) return e; }          \
         else sdf_forward_tc_a_kernel<CC><<<grid, TCF_THREADS, smem_a, st>>>(*net, ls, pa, x, P, flags, sdf, feat_fm, Z, DYDX, H0); \
-        if (split & 2u) { if (int e = launch_tcs_b(net, x, P, flags, grad, Z, R, DYDX, st)) return e; }                     \
+        if (split & 2u) { if (int e = launch_tcs_b(net, x, P, flags, grad, Z, R, DYDX, pe_h0, st)) return e; }                     \
         else sdf_forward_tc_b_kernel<CC><<<grid, TCF_THREADS, smem_b, st>>>(*net, ls, pb, x, P, flags, grad, Z, R, DYDX);   \
     } while (0)
     switch (net->grid.C) {
@@ -537,10 +541,12 @@ int launch_grid_scatter(const nicer_grid_t *g, const float *x, uint32_t P, const
                         const float *g_grad, float *grad_table, cudaStream_t st);
 
 int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
-                           const float *DYDX, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
+                           const float *DYDX, const float *H0, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
                            float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, cudaStream_t st,
                            cudaStream_t scatter_st) {
     const unsigned split = tc_split_mask();
+    static const bool pe_reload = [] { const char *e = getenv("NICER_PE_RELOAD"); return !(e && e[0] == '0'); }();
+    const float *pe_h0 = pe_reload ? H0 : nullptr;
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t pairs = div_up(div_up(P, 128), 2);
     const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
@@ -552,9 +558,9 @@ int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t 
                    "nicer_sdf_backward(tc T)");                                                                          \
         NICER_CUDA(cudaFuncSetAttribute(sdf_backward_tc_r_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r), \
                    "nicer_sdf_backward(tc R)");                                                                          \
-        if (split & 4u) { if (int e = launch_tcs_t(net, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0, st)) return e; }      \
+        if (split & 4u) { if (int e = launch_tcs_t(net, x, P, Z, R, DYDX, pe_h0, g_grad, ZB, QB, AB, TAN, T0, st)) return e; } \
         else sdf_backward_tc_t_kernel<CC><<<grid, TCF_THREADS, smem_t, st>>>(*net, ls, pt, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0); \
-        if (split & 8u) { if (int e = launch_tcs_r(net, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, ZB, QB, GY, st)) return e; } \
+        if (split & 8u) { if (int e = launch_tcs_r(net, x, P, Z, DYDX, pe_h0, g_sdf, g_feat_fm, g_grad, grad_x, ZB, QB, GY, st)) return e; } \
         else sdf_backward_tc_r_kernel<CC><<<grid, TCF_THREADS, smem_r, st>>>(*net, ls, pr, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, \
                                                                         ZB, QB, GY);                                     \
     } while (0)

@@ -225,7 +225,9 @@ sdf_forward_tcs_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
 template <int C>
 __global__ void __launch_bounds__(TCS_THREADS, 1)
 sdf_forward_tcs_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
-                         uint32_t P, uint32_t flags, float *grad, const float *Z, float *R, const float *DYDX) {
+                         uint32_t P, uint32_t flags, float *grad, const float *Z, float *R, const float *DYDX,
+                         const float *__restrict__ H0) {
+    // H0 != NULL: rows 3..38 hold sin / cos (2^f x_d) as kernel A wrote them; reading them back replaces 18 sincosf per point
     extern __shared__ __align__(16) float smem[];
     __shared__ TcsShared sh;
     LevelInfo *lv;
@@ -269,7 +271,20 @@ sdf_forward_tcs_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
         }
         mat_issue2(t, pl, 0, smem);              // r_0 = W_0^T q_1   (80 columns: [32 grid | 39 PE | pad])
         if (h == 1) {
-            const float x[3] = {__ldg(X + 3 * (size_t)p), __ldg(X + 3 * (size_t)p + 1), __ldg(X + 3 * (size_t)p + 2)};
+            float sc[36];   // sin / cos (2^f x_d) in the order of the input vector: [6 f + d] sin, [6 f + 3 + d] cos
+            if (H0) {
+#pragma unroll
+                for (int k = 0; k < 36; ++k) sc[k] = __ldg(H0 + (size_t)(3 + k) * Ps + p);
+            } else {
+                const float x[3] = {__ldg(X + 3 * (size_t)p), __ldg(X + 3 * (size_t)p + 1), __ldg(X + 3 * (size_t)p + 2)};
+                float fr = 1.0f;
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) sincosf(x[d] * fr, &sc[6 * f + d], &sc[6 * f + 3 + d]);
+                    fr *= 2.0f;
+                }
+            }
             gemm_wait(t);
             float rp[40];   // PE part: columns 32..71
 #pragma unroll
@@ -280,11 +295,7 @@ sdf_forward_tcs_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
 #pragma unroll
             for (int f = 0; f < 6; ++f) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    float s, c;
-                    sincosf(x[d] * fr, &s, &c);
-                    g[d] += fr * (c * rp[3 + 6 * f + d] - s * rp[3 + 6 * f + 3 + d]);
-                }
+                for (int d = 0; d < 3; ++d) g[d] += fr * (sc[6 * f + 3 + d] * rp[3 + 6 * f + d] - sc[6 * f + d] * rp[3 + 6 * f + 3 + d]);
                 fr *= 2.0f;
             }
             tile_sync2(t);                       // grid part of d sdf/dx from the other half
@@ -329,8 +340,9 @@ sdf_forward_tcs_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
 template <int C>
 __global__ void __launch_bounds__(TCS_THREADS, 1)
 sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
-                          uint32_t P, const float *Z, const float *R, const float *DYDX, const float *g_grad, float *ZB,
-                          float *QB, float *AB, float *TAN, float *T0) {
+                          uint32_t P, const float *Z, const float *R, const float *DYDX, const float *__restrict__ H0,
+                          const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0) {
+    // H0 != NULL: sin / cos of the positional encoding are read back from the saved input (rows 3..38) instead of recomputed
     extern __shared__ __align__(16) float smem[];
     __shared__ TcsShared sh;
     LevelInfo *lv;
@@ -350,7 +362,6 @@ sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
         if (g_grad) { gg[0] = g_grad[3 * (size_t)p]; gg[1] = g_grad[3 * (size_t)p + 1]; gg[2] = g_grad[3 * (size_t)p + 2]; }
         if (h == 1) {
             // ---- t_0: PE part (columns 32..70), rows 0..38 of T0
-            const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
             float tp[48];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
@@ -360,7 +371,15 @@ sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 float sc[12];
-                pe_sincos<6, true>(x[d], sc);
+                if (H0) {
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) {
+                        sc[2 * f] = __ldg(H0 + (size_t)(3 + 6 * f + d) * Ps + p);
+                        sc[2 * f + 1] = __ldg(H0 + (size_t)(3 + 6 * f + 3 + d) * Ps + p);
+                    }
+                } else {
+                    pe_sincos<6, true>(X[3 * (size_t)p + d], sc);
+                }
                 float fr = 1.0f;
 #pragma unroll
                 for (int f = 0; f < 6; ++f) {
@@ -400,44 +419,44 @@ sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
         }
         mat_issue2(t, pl, 0, smem);   // u_1 = W_0 t_0
         for (int l = 1; l <= n; ++l) {
-            // z_l rows prefetched under the MMAs; the r_l rows follow one 8-column chunk ahead of their use (both sets of 32 plus
-            // the four output streams do not fit 128 registers: ptxas spilled the loaded values, i.e. waited for every load)
-            float zv[32], rc[8];
+            // z_l and r_l rows in 8-column chunks, two chunks ahead of their use (the first two are issued under the MMAs): with
+            // both sets of 32 prefetched plus the four output streams ptxas spilled the loaded values, i.e. waited for every load
+            float zq[4][8], rq[4][8];
             const size_t row0 = (size_t)(l - 1) * NICER_W + c0 * 8;
-            load32(Z, row0, Ps, p, zv);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rc[i] = (l < n) ? __ldg(R + (row0 + i) * Ps + p) : wl[i];
+#define T_LOAD(CH)                                                                                                     \
+    do {                                                                                                               \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                                                \
+            zq[CH][i] = __ldg(Z + (row0 + (CH) * 8 + i) * Ps + p);                                                     \
+            rq[CH][i] = (l < n) ? __ldg(R + (row0 + (CH) * 8 + i) * Ps + p) : wl[(CH) * 8 + i];                        \
+        }                                                                                                              \
+    } while (0)
+            T_LOAD(0);
+            T_LOAD(1);
             gemm_wait(t);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
-                float v[8], rn[8];
-                if (c8 < 3) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rn[i] = (l < n) ? __ldg(R + (row0 + (c8 + 1) * 8 + i) * Ps + p) : wl[(c8 + 1) * 8 + i];
-                }
+                float v[8];
+                if (c8 == 0) T_LOAD(2);
+                if (c8 == 1) T_LOAD(3);
                 ld_d8(t, c0 + c8, v);
                 tc::wait_ld();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int j = c8 * 8 + i;
-                    const size_t o = (row0 + j) * Ps + p;
-                    const SpEval sp = sp_eval(zv[j]);
+                    const size_t o = (row0 + c8 * 8 + i) * Ps + p;
+                    const SpEval sp = sp_eval(zq[c8][i]);
                     const float u = v[i];
                     const float tan = u * sp.s1;
                     if (valid) {
                         TAN[o] = tan;
-                        QB[o] = rc[i] * sp.s1;
+                        QB[o] = rq[c8][i] * sp.s1;
                         AB[o] = sp.a;
-                        ZB[o] = u * rc[i] * sp.s2;
+                        ZB[o] = u * rq[c8][i] * sp.s2;
                     }
                     v[i] = tan;
                 }
                 if (l < n) st_a8(t, c0 + c8, v);
-                if (c8 < 3) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rc[i] = rn[i];
-                }
             }
+#undef T_LOAD
             if (l < n) mat_issue2(t, pl, l, smem);   // u_{l+1} = W_l tan_l
         }
     }
@@ -450,8 +469,8 @@ sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
 template <int C>
 __global__ void __launch_bounds__(TCS_THREADS, 1)
 sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
-                          uint32_t P, const float *Z, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
-                          const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY) {
+                          uint32_t P, const float *Z, const float *DYDX, const float *__restrict__ H0, const float *g_sdf,
+                          const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY) {
     extern __shared__ __align__(16) float smem[];
     __shared__ TcsShared sh;
     LevelInfo *lv;
@@ -503,12 +522,20 @@ sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
             float q1[32];
             load32(QB, (size_t)c0 * 8, Ps, p, q1);
             // ---- PE part of hbar_0 and of r_0 -> dL/dx
-            const float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
             float gg[3] = {0.f, 0.f, 0.f};
             if (g_grad) { gg[0] = g_grad[3 * (size_t)p]; gg[1] = g_grad[3 * (size_t)p + 1]; gg[2] = g_grad[3 * (size_t)p + 2]; }
+            float pesc[36];     // sin/cos of the PE ([12 d + 2 f] sin, [12 d + 2 f + 1] cos), used for both terms below
+            if (H0) {           // read back what kernel A saved (in flight under the MMAs) instead of recomputing
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) {
+                        pesc[12 * d + 2 * f] = __ldg(H0 + (size_t)(3 + 6 * f + d) * Ps + p);
+                        pesc[12 * d + 2 * f + 1] = __ldg(H0 + (size_t)(3 + 6 * f + 3 + d) * Ps + p);
+                    }
+            }
             gemm_wait(t);
             float xb[3];
-            float pesc[36];     // sin/cos of the PE, reused for the second-order term below
             {
                 float hp[40];
 #pragma unroll
@@ -517,7 +544,7 @@ sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
                 xb[0] = hp[0]; xb[1] = hp[1]; xb[2] = hp[2];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    pe_sincos<6, true>(x[d], &pesc[12 * d]);
+                    if (!H0) pe_sincos<6, true>(X[3 * (size_t)p + d], &pesc[12 * d]);
                     float fr = 1.0f;
 #pragma unroll
                     for (int f = 0; f < 6; ++f) {
@@ -640,32 +667,34 @@ int launch_tcs_a(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_
 }
 
 int launch_tcs_b(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *grad, const float *Z, float *R,
-                 const float *DYDX, cudaStream_t st) {
+                 const float *DYDX, const float *H0, cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t grid = tcs_grid(P);
     const TcfPlan pl = plan_b(net);
     const size_t smem = (size_t)pl.total_floats * sizeof(float);
-    TCS_DISPATCH(sdf_forward_tcs_b_kernel, smem, "nicer_sdf_forward(tcs B)", *net, ls, pl, x, P, flags, grad, Z, R, DYDX);
+    TCS_DISPATCH(sdf_forward_tcs_b_kernel, smem, "nicer_sdf_forward(tcs B)", *net, ls, pl, x, P, flags, grad, Z, R, DYDX, H0);
     return 0;
 }
 
 int launch_tcs_t(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R, const float *DYDX,
-                 const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st) {
+                 const float *H0, const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t grid = tcs_grid(P);
     const TcfPlan pl = plan_t(net);
     const size_t smem = (size_t)pl.total_floats * sizeof(float);
-    TCS_DISPATCH(sdf_backward_tcs_t_kernel, smem, "nicer_sdf_backward(tcs T)", *net, ls, pl, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0);
+    TCS_DISPATCH(sdf_backward_tcs_t_kernel, smem, "nicer_sdf_backward(tcs T)", *net, ls, pl, x, P, Z, R, DYDX, H0, g_grad, ZB, QB, AB, TAN,
+                 T0);
     return 0;
 }
 
-int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *DYDX, const float *g_sdf,
-                 const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY, cudaStream_t st) {
+int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *DYDX, const float *H0,
+                 const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY,
+                 cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t grid = tcs_grid(P);
     const TcfPlan pl = plan_r(net);
     const size_t smem = (size_t)pl.total_floats * sizeof(float);
-    TCS_DISPATCH(sdf_backward_tcs_r_kernel, smem, "nicer_sdf_backward(tcs R)", *net, ls, pl, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad,
+    TCS_DISPATCH(sdf_backward_tcs_r_kernel, smem, "nicer_sdf_backward(tcs R)", *net, ls, pl, x, P, Z, DYDX, H0, g_sdf, g_feat_fm, g_grad,
                  grad_x, ZB, QB, GY);
     return 0;
 }

@@ -101,7 +101,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
 }
 
 extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
-                                  const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
+                                  const float *R, const float *DYDX, const float * /*H0*/, const float *g_sdf, const float *g_feat_fm,
                                   const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
                                   float *AB, float *TAN, float *T0, float * /*GY*/, void *, void *) {
     HostSdf h(*net);
@@ -703,8 +703,9 @@ extern "C" int nicer_warp_gt(const float *uvp, const float *img, const float *de
     return 0;
 }
 
+extern "C" size_t nicer_masked_l1_mean_workspace(void) { return 16; }
 extern "C" int nicer_masked_l1_mean(const float *a, const float *b, const unsigned char *mask, uint32_t n_mask, uint32_t inner,
-                                    uint32_t b_len, float *out, void *) {
+                                    uint32_t b_len, void *, float *out, void *) {
     double sum = 0.0, cnt = 0.0;
     for (uint32_t m = 0; m < n_mask; ++m) {
         if (!mask[m]) continue;
