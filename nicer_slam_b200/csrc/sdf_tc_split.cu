@@ -14,93 +14,16 @@
 // the per-tile dependent chain between two MMA groups is half as long.  The few per-point scalars that need both halves
 // (sdf = w_n . a_n, d sdf/dx, dL/dx) cross through a 2 KB shared-memory hand-over, ordered by the tile's named barrier.
 #include "sdf_tc_plan.cuh"
+#include "tc_tile2.cuh"
 
 namespace nicer {
 
-constexpr int TCS_THREADS = 512;
-
-struct TcsShared {
-    uint64_t bars[2];
-    uint32_t tmem_slot;
-    float xch[2][128][4];     // [tile][point][..]: partial results handed from one column half to the other
-};
-
-__device__ __forceinline__ void tile_sync2(const Tile &t) { asm volatile("bar.sync %0, 256;" ::"r"(t.id) : "memory"); }
-
-// as gemm_issue (tc_tile.cuh) for a 256-thread tile
-__device__ __forceinline__ void gemm_issue2(Tile &t, uint32_t whi, uint32_t wlo, int K, int N) {
-    tc::wait_st();
-    tc::fence_before_sync();
-    tile_sync2(t);
-    if (t.leader) {
-        tc::fence_after_sync();
-        const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)N);
-        const uint32_t chunk = (uint32_t)N * 16u;
-        for (int ks = 0; ks < K / 8; ++ks) {
-            const uint64_t bhi = tc::smem_desc(whi + (uint32_t)ks * 2u * chunk, chunk, 128u);
-            const uint64_t blo = tc::smem_desc(wlo + (uint32_t)ks * 2u * chunk, chunk, 128u);
-            const uint32_t ahi = t.tmem + ks * 8, alo = t.tmem + t.alo + ks * 8;
-            tc::mma_tf32_ts(t.tmem + t.dcol, ahi, bhi, idesc, ks > 0 ? 1u : 0u);
-            tc::mma_tf32_ts(t.tmem + t.dcol, alo, bhi, idesc, 1u);
-            tc::mma_tf32_ts(t.tmem + t.dcol, ahi, blo, idesc, 1u);
-        }
-        tc::mma_commit(t.bar);
-    }
-}
 __device__ __forceinline__ void mat_issue2(Tile &t, const TcfPlan &pl, int i, float *smem) {
     gemm_issue2(t, tc::smem_u32(smem + pl.m[i].hi), tc::smem_u32(smem + pl.m[i].lo), pl.m[i].K, pl.m[i].rows);
 }
 __device__ __forceinline__ void mat_gemm2(Tile &t, const TcfPlan &pl, int i, float *smem) {
     mat_issue2(t, pl, i, smem);
     gemm_wait(t);
-}
-
-// barriers + TMEM of a two-tile, 512-thread CTA; returns the calling thread's tile. Call after the operands are staged.
-__device__ __forceinline__ Tile tile_setup2(TcsShared &sh) {
-    const int tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) { tc::mbar_init(&sh.bars[0], 1); tc::mbar_init(&sh.bars[1], 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc(&sh.tmem_slot, TCF_TMEM);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    Tile t;
-    const int tile = tid >> 8;
-    t.tmem = sh.tmem_slot + (uint32_t)tile * TCF_TILE_COLS;
-    t.lane_base = t.tmem + ((uint32_t)((warp & 3) * 32) << 16);     // warps w and w + 4 of a tile: same lane quarter
-    t.bar = &sh.bars[tile];
-    t.parity = 0;
-    t.id = 1 + tile;
-    t.leader = (tid & 255) == 0;
-    t.alo = TCF_ALO;
-    t.dcol = TCF_D;
-    return t;
-}
-
-__device__ __forceinline__ void tile_teardown2(TcsShared &sh) {
-    tc::fence_before_sync();
-    __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(sh.tmem_slot, TCF_TMEM);
-}
-
-// 32 values of one saved layer row-block (this thread's column half) for this point, issued together
-__device__ __forceinline__ void load32(const float *__restrict__ base, size_t row0, size_t Ps, uint32_t p, float v[32]) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __ldg(base + (row0 + j) * Ps + p);
-}
-__device__ __forceinline__ void load32_rw(const float *base, size_t row0, size_t Ps, uint32_t p, float v[32]) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = base[(row0 + j) * Ps + p];
-}
-// this thread's four accumulator chunks (32 columns starting at 32 h)
-__device__ __forceinline__ void ld_half(const Tile &t, int c0, float v[32]) {
-#pragma unroll
-    for (int c8 = 0; c8 < 4; ++c8) ld_d8(t, c0 + c8, &v[c8 * 8]);
-    tc::wait_ld();
-}
-__device__ __forceinline__ void st_half(const Tile &t, int c0, const float v[32]) {
-#pragma unroll
-    for (int c8 = 0; c8 < 4; ++c8) st_a8(t, c0 + c8, &v[c8 * 8]);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel A
@@ -113,7 +36,7 @@ sdf_forward_tcs_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
     __shared__ TcsShared sh;
     LevelInfo *lv;
     tcf_stage_all(net, ls, pl, smem, lv);
-    Tile t = tile_setup2(sh);
+    Tile t = tile_setup2(sh, TCF_ALO, TCF_D);
     const int n = (int)net.n_hidden, L = (int)net.grid.L;
     const int h = (threadIdx.x >> 7) & 1, c0 = 4 * h, tile = threadIdx.x >> 8, lane = threadIdx.x & 127;
     const size_t Ps = P;
@@ -232,7 +155,7 @@ sdf_forward_tcs_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
     __shared__ TcsShared sh;
     LevelInfo *lv;
     tcf_stage_all(net, ls, pl, smem, lv);
-    Tile t = tile_setup2(sh);
+    Tile t = tile_setup2(sh, TCF_ALO, TCF_D);
     const int n = (int)net.n_hidden, L = (int)net.grid.L;
     const int h = (threadIdx.x >> 7) & 1, c0 = 4 * h, tile = threadIdx.x >> 8, lane = threadIdx.x & 127;
     const size_t Ps = P;
@@ -347,7 +270,7 @@ sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
     __shared__ TcsShared sh;
     LevelInfo *lv;
     tcf_stage_all(net, ls, pl, smem, lv);
-    Tile t = tile_setup2(sh);
+    Tile t = tile_setup2(sh, TCF_ALO, TCF_D);
     const int n = (int)net.n_hidden, L = (int)net.grid.L;
     const int h = (threadIdx.x >> 7) & 1, c0 = 4 * h, tile = threadIdx.x >> 8, lane = threadIdx.x & 127;
     const size_t Ps = P;
@@ -475,7 +398,7 @@ sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
     __shared__ TcsShared sh;
     LevelInfo *lv;
     tcf_stage_all(net, ls, pl, smem, lv);
-    Tile t = tile_setup2(sh);
+    Tile t = tile_setup2(sh, TCF_ALO, TCF_D);
     const int n = (int)net.n_hidden, L = (int)net.grid.L;
     const int h = (threadIdx.x >> 7) & 1, c0 = 4 * h, tile = threadIdx.x >> 8, lane = threadIdx.x & 127;
     const size_t Ps = P;
