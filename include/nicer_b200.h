@@ -113,6 +113,8 @@ int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, ui
  *     ZB  [n_hidden*64][P]  dL/dz_l          QB  [n_hidden*64][P]  q_l = r_l * softplus'(z_l)
  *     AB  [n_hidden*64][P]  a_l              TAN [n_hidden*64][P]  tangent of a_l in direction g_grad
  *     T0  [d_in][P]         tangent of the network input (H0, the input itself, is saved by the forward)
+ *     tan_sum [64] | NULL   accumulated (+=): sum over the points of tan_n, the second-order part of dL/dW_n[0,:] (the sdf row
+ *                           of the last layer), so that the caller needs no separate reduction over TAN
  *   Workspace: GY [2*L*C][P]  dL/d(enc) (first-order rows, then the second-order rows) handed from the MLP backward
  *                             kernel to the grid-scatter kernel
  */
@@ -120,7 +122,7 @@ int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P,
                        const float *Z, const float *R, const float *DYDX, const float *H0,
                        const float *g_sdf, const float *g_feat_fm, const float *g_grad,
                        float *grad_x, float *grad_table,
-                       float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, void *stream,
+                       float *ZB, float *QB, float *AB, float *TAN, float *T0, float *tan_sum, float *GY, void *stream,
                        void *scatter_stream);
 /* scatter_stream (both backward calls): stream the grid-scatter kernel runs on, after everything enqueued on `stream`
  * by the call (NULL or == stream: same stream).  grad_table is complete when scatter_stream has drained; the caller

@@ -142,8 +142,30 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
 
 int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
                            const float *DYDX, const float *H0, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
-                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, cudaStream_t st,
-                           cudaStream_t scatter_st);
+                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *tan_sum, float *GY,
+                           cudaStream_t st, cudaStream_t scatter_st);
+
+// out[r] += sum_p rows[r][p]   (one block per row)
+__global__ void __launch_bounds__(256) row_sum_accum_kernel(const float *__restrict__ rows, uint32_t P, float *out) {
+    const float *row = rows + (size_t)blockIdx.x * P;
+    float a = 0.f;
+    for (uint32_t p = threadIdx.x; p < P; p += 256) a += row[p];
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(out + blockIdx.x, t);
+    }
+}
+int launch_row_sum_accum(const float *rows, uint32_t n_rows, uint32_t P, float *out, cudaStream_t st) {
+    row_sum_accum_kernel<<<n_rows, 256, 0, st>>>(rows, P, out);
+    NICER_CHECK_LAUNCH("nicer_sdf_backward(tan sum)");
+    return 0;
+}
 
 template <typename K>
 static int prep_kernel(K kernel, size_t smem_bytes, const char *who) {
@@ -196,7 +218,8 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
 extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
                                   const float *R, const float *DYDX, const float *H0, const float *g_sdf, const float *g_feat_fm,
                                   const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
-                                  float *AB, float *TAN, float *T0, float *GY, void *stream, void *scatter_stream) {
+                                  float *AB, float *TAN, float *T0, float *tan_sum, float *GY, void *stream,
+                                  void *scatter_stream) {
     if (int e = check_sdf_net(net, "nicer_sdf_backward")) return e;
     if (P == 0) return 0;
     if (!x || !Z || !DYDX || !ZB || !QB || !AB || !TAN || !T0)      /* grad_table may be NULL: no table gradient wanted */
@@ -206,7 +229,7 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
     if (tc_enabled() && net->multires == 6 && !GY) NICER_FAIL(-1, "nicer_sdf_backward: GY workspace is NULL");
     if (tc_enabled() && net->multires == 6)
         return launch_sdf_backward_tc(net, x, P, Z, R, DYDX, H0, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB, TAN, T0,
-                                      GY, (cudaStream_t)stream, (cudaStream_t)scatter_stream);
+                                      tan_sum, GY, (cudaStream_t)stream, (cudaStream_t)scatter_stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);
@@ -226,5 +249,6 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
     }
 #undef LAUNCH
     NICER_CHECK_LAUNCH("nicer_sdf_backward");
+    if (tan_sum) return launch_row_sum_accum(TAN + (size_t)(net->n_hidden - 1) * NICER_W * P, NICER_W, P, tan_sum, st);
     return 0;
 }

@@ -250,7 +250,9 @@ int launch_tcs_a(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_
 int launch_tcs_b(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *grad, const float *Z, float *R,
                  const float *DYDX, const float *H0, cudaStream_t st);
 int launch_tcs_t(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R, const float *DYDX,
-                 const float *H0, const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st);
+                 const float *H0, const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *tan_sum,
+                 cudaStream_t st);
+int launch_row_sum_accum(const float *rows, uint32_t n_rows, uint32_t P, float *out, cudaStream_t st);
 int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *DYDX, const float *H0,
                  const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY,
                  cudaStream_t st);
@@ -542,8 +544,8 @@ int launch_grid_scatter(const nicer_grid_t *g, const float *x, uint32_t P, const
 
 int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
                            const float *DYDX, const float *H0, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
-                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *GY, cudaStream_t st,
-                           cudaStream_t scatter_st) {
+                           float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *tan_sum, float *GY,
+                           cudaStream_t st, cudaStream_t scatter_st) {
     const unsigned split = tc_split_mask();
     static const bool pe_reload = [] { const char *e = getenv("NICER_PE_RELOAD"); return !(e && e[0] == '0'); }();
     const float *pe_h0 = pe_reload ? H0 : nullptr;
@@ -558,7 +560,7 @@ int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t 
                    "nicer_sdf_backward(tc T)");                                                                          \
         NICER_CUDA(cudaFuncSetAttribute(sdf_backward_tc_r_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r), \
                    "nicer_sdf_backward(tc R)");                                                                          \
-        if (split & 4u) { if (int e = launch_tcs_t(net, x, P, Z, R, DYDX, pe_h0, g_grad, ZB, QB, AB, TAN, T0, st)) return e; } \
+        if (split & 4u) { if (int e = launch_tcs_t(net, x, P, Z, R, DYDX, pe_h0, g_grad, ZB, QB, AB, TAN, T0, tan_sum, st)) return e; } \
         else sdf_backward_tc_t_kernel<CC><<<grid, TCF_THREADS, smem_t, st>>>(*net, ls, pt, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0); \
         if (split & 8u) { if (int e = launch_tcs_r(net, x, P, Z, DYDX, pe_h0, g_sdf, g_feat_fm, g_grad, grad_x, ZB, QB, GY, st)) return e; } \
         else sdf_backward_tc_r_kernel<CC><<<grid, TCF_THREADS, smem_r, st>>>(*net, ls, pr, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, \
@@ -571,6 +573,9 @@ int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t 
     }
 #undef LAUNCH
     NICER_CHECK_LAUNCH("nicer_sdf_backward(tc)");
+    if (tan_sum && !(split & 4u)) {      // the one-thread-per-point tangent kernel does not sum tan_n itself
+        if (int e = launch_row_sum_accum(TAN + (size_t)(net->n_hidden - 1) * NICER_W * P, NICER_W, P, tan_sum, st)) return e;
+    }
     if (scatter_st && scatter_st != st) {
         if (int e = stream_fork(st, scatter_st)) return e;
     } else {

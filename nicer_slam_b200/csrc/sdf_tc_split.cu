@@ -258,16 +258,36 @@ sdf_forward_tcs_b_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
     tile_teardown2(sh);
 }
 
+// Sums of 8 per-lane values over the 32 lanes of a warp with 9 shuffles (halving exchange, then two butterfly steps): every
+// lane returns the warp total of column `col` (lanes that differ only in their two low bits hold the same column).
+__device__ __forceinline__ float warp_colsum8(const float v[8], int lane, int &col) {
+    const bool u4 = (lane & 16) != 0, u2 = (lane & 8) != 0, u1 = (lane & 4) != 0;
+    float a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = (u4 ? v[4 + i] : v[i]) + __shfl_xor_sync(0xffffffffu, u4 ? v[i] : v[4 + i], 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) b[i] = (u2 ? a[2 + i] : a[i]) + __shfl_xor_sync(0xffffffffu, u2 ? a[i] : a[2 + i], 8);
+    float c = (u1 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, u1 ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    col = (u4 ? 4 : 0) + (u2 ? 2 : 0) + (u1 ? 1 : 0);
+    return c;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel T
 // tangent pass: t_0 = J g_bar, u_1 = W_0 t_0, tan_l = u_l * sp'(z_l), u_{l+1} = W_l tan_l; writes TAN, QB, AB, ZB, T0
 template <int C>
 __global__ void __launch_bounds__(TCS_THREADS, 1)
 sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
                           uint32_t P, const float *Z, const float *R, const float *DYDX, const float *__restrict__ H0,
-                          const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0) {
+                          const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *tan_sum) {
     // H0 != NULL: sin / cos of the positional encoding are read back from the saved input (rows 3..38) instead of recomputed
+    // tan_sum != NULL: [64] += sum over the points of tan_n (the second-order part of dL/dW_n[0,:], i.e. of the sdf row of the
+    //                  last layer): column sums per warp by shuffles, per CTA in shared memory, one atomic per column at the end
     extern __shared__ __align__(16) float smem[];
     __shared__ TcsShared sh;
+    __shared__ float colsum_s[NICER_W];
+    if (threadIdx.x < NICER_W) colsum_s[threadIdx.x] = 0.f;
     LevelInfo *lv;
     tcf_stage_all(net, ls, pl, smem, lv);
     Tile t = tile_setup2(sh, TCF_ALO, TCF_D);
@@ -377,13 +397,24 @@ sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
                     }
                     v[i] = tan;
                 }
-                if (l < n) st_a8(t, c0 + c8, v);
+                if (l < n) {
+                    st_a8(t, c0 + c8, v);
+                } else if (tan_sum) {
+                    if (!valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                    }
+                    int col;
+                    const float cs = warp_colsum8(v, threadIdx.x & 31, col);
+                    if ((threadIdx.x & 3) == 0) atomicAdd(&colsum_s[(c0 + c8) * 8 + col], cs);
+                }
             }
 #undef T_LOAD
             if (l < n) mat_issue2(t, pl, l, smem);   // u_{l+1} = W_l tan_l
         }
     }
     tile_teardown2(sh);
+    if (tan_sum && threadIdx.x < NICER_W) atomicAdd(tan_sum + threadIdx.x, colsum_s[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel R
@@ -600,13 +631,14 @@ int launch_tcs_b(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_
 }
 
 int launch_tcs_t(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R, const float *DYDX,
-                 const float *H0, const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, cudaStream_t st) {
+                 const float *H0, const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *tan_sum,
+                 cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t grid = tcs_grid(P);
     const TcfPlan pl = plan_t(net);
     const size_t smem = (size_t)pl.total_floats * sizeof(float);
     TCS_DISPATCH(sdf_backward_tcs_t_kernel, smem, "nicer_sdf_backward(tcs T)", *net, ls, pl, x, P, Z, R, DYDX, H0, g_grad, ZB, QB, AB, TAN,
-                 T0);
+                 T0, tan_sum);
     return 0;
 }
 

@@ -325,15 +325,17 @@ class SdfNetFn(torch.autograd.Function):
         GY = torch.empty(2 * meta.grid.L * meta.grid.C, P, device=dev)     # MLP-backward -> grid-scatter hand-over
         net = _sdf_struct(meta, table, offsets, wb)
         side = _scatter_stream(dev)
+        zeros = _zeros_like_many(list(wb)) if need_w else None        # dW_0, db_0, dW_1, ... in one buffer
+        # the tangent kernel adds sum_p tan_n (second-order part of the sdf row of dW_n) straight into dW_n[0, :]
+        tan_sum = zeros[2 * n][0] if need_w else None
         check(lib().nicer_sdf_backward(C.byref(net), ptr(x), P, ptr(Z), ptr(R), ptr(DYDX), ptr(H0), ptr(gs), ptr(gf), ptr(gg),
                                        ptr(grad_x), ptr(grad_table), ptr(ZB), ptr(QB), ptr(AB), ptr(TAN),
-                                       ptr(T0), ptr(GY), stream(), _sptr(side)), "nicer_sdf_backward")
+                                       ptr(T0), ptr(tan_sum), ptr(GY), stream(), _sptr(side)), "nicer_sdf_backward")
         if not need_w:
             _join(side, None, defer=False)
             return (grad_x, grad_table, None, None, None, *([None] * len(wb)))
         grads = []
         oa = OuterAccumBatch()
-        zeros = _zeros_like_many(list(wb))         # dW_0, db_0, dW_1, ... in one buffer
         for l in range(n + 1):
             W = wb[2 * l]
             dW, db = zeros[2 * l], zeros[2 * l + 1]
@@ -349,7 +351,6 @@ class SdfNetFn(torch.autograd.Function):
                     oa.add(gs.view(1, P), a_n, dW[:1], db[:1])
                 if gf is not None and nfeat > 0:
                     oa.add(gf[:nfeat], a_n, dW[1:], db[1:])
-                dW[0] += TAN[(n - 1) * HIDDEN:].sum(dim=1)
             grads += [dW, db]
         oa.flush()
         _join(side, None, defer=False)       # the scatter overlapped with the weight-gradient GEMMs above
