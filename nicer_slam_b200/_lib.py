@@ -137,6 +137,11 @@ def require(t, dtype=torch.float32, name="tensor"):
     """Device/contiguity/dtype guard (the reference's CHECK_CUDA / CHECK_CONTIGUOUS, hashencoder.cu:16-19)."""
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's stream (stream() below); a tensor of another device would be read through
+        # peer access at best.  One process per GPU (torch.cuda.set_device(rank)) is the supported layout.
+        raise RuntimeError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                           "call torch.cuda.set_device() (one process per GPU)")
     if not t.is_contiguous():
         raise RuntimeError(f"{name} must be a contiguous tensor")
     if t.dtype != dtype:
