@@ -698,7 +698,7 @@ def kernel_breakdown(step, dev, P, S):
     sdf_out = torch.empty(U, device=dev)
 
     def mlp_only(flags):
-        _lib.check(_lib.lib().nicer_sdf_forward(C.byref(net), _lib.ptr(xu), U, flags, _lib.ptr(sdf_out), None, None, None, None,
+        _lib.check(_lib.lib().nicer_sdf_forward(C.byref(net), _lib.ptr(xu), U, 0, flags, _lib.ptr(sdf_out), None, None, None, None,
                                                 None, _lib.ptr(ws), _lib.stream()), "nicer_sdf_forward")
     mlp_only(ops.F_SDF_ONLY)
     t_dom = timed(lambda: mlp_only(ops.F_SDF_ONLY | 8))

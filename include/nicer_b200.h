@@ -100,13 +100,16 @@ typedef struct {
 #define NICER_SDF_ACCUMULATE 2u  /* add into sdf/feat/grad instead of overwriting (coarse+fine sum, base_networks.py:40) */
 #define NICER_SDF_NO_FEAT 4u     /* gradient() path: sdf + gradient only (base_networks.py:195-206) */
 
-int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags,
-                      float *sdf /*[P]*/, float *feat_fm /*[64][P]*/, float *grad /*[P,3]*/,
+/* P_feat (both calls): only the first P_feat points carry features and upstream sdf / feature gradients -- feat_fm, g_feat_fm are
+ * [64][P_feat] and g_sdf is [P_feat]; the points behind them (the eikonal samples of network.py:313-336 batched behind the
+ * main-pass points, which only need d sdf/dx) skip the feature head.  0 means P (every point). */
+int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t P_feat, uint32_t flags,
+                      float *sdf /*[P]*/, float *feat_fm /*[64][P_feat]*/, float *grad /*[P,3]*/,
                       float *Z, float *R, float *DYDX, float *H0, void *stream);
 
 /* Backward of (sdf, feat, grad) w.r.t. x, the grid and (through the workspace below) the weights.
  *   H0 [d_in][P] | NULL       the saved network input (its x / positional-encoding rows are read back instead of recomputed)
- *   g_sdf [P] | NULL, g_feat_fm [64][P] | NULL, g_grad [P,3] | NULL   upstream gradients
+ *   g_sdf [P_feat] | NULL, g_feat_fm [64][P_feat] | NULL, g_grad [P,3] | NULL   upstream gradients
  *   grad_x [P,3] | NULL       accumulated (+=)
  *   grad_table [n_entries,C]  accumulated with atomics (first- and second-order terms both land here)
  *   Outputs for nicer_outer_accum (all fm, written):
@@ -118,7 +121,7 @@ int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, ui
  *   Workspace: GY [2*L*C][P]  dL/d(enc) (first-order rows, then the second-order rows) handed from the MLP backward
  *                             kernel to the grid-scatter kernel
  */
-int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P,
+int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t P_feat,
                        const float *Z, const float *R, const float *DYDX, const float *H0,
                        const float *g_sdf, const float *g_feat_fm, const float *g_grad,
                        float *grad_x, float *grad_table,

@@ -58,8 +58,8 @@ _SIGS = {
                                    _fp, _fp],
     "nicer_hash_encode_second_backward": [_fp, _fp, _fp, _fp, _u32, _u32, _u32, _u32, C.c_float, _u32, C.c_int, _fp,
                                           _fp, _fp, _fp, _fp],
-    "nicer_sdf_forward": [C.POINTER(SdfNetT), _fp, _u32, _u32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
-    "nicer_sdf_backward": [C.POINTER(SdfNetT), _fp, _u32] + [_fp] * 18,
+    "nicer_sdf_forward": [C.POINTER(SdfNetT), _fp, _u32, _u32, _u32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
+    "nicer_sdf_backward": [C.POINTER(SdfNetT), _fp, _u32, _u32] + [_fp] * 18,
     "nicer_color_forward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32, _fp, _fp, _fp, _fp, _fp],
     "nicer_color_backward": [C.POINTER(ColorNetT), _fp, _fp, _fp, _fp, _u32] + [_fp] * 14,
     "nicer_outer_accum": [_fp, _u32, _u32, _fp, _u32, _u32, _u32, _fp, _u32, _fp, _fp],

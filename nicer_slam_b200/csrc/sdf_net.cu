@@ -86,7 +86,7 @@ __device__ void stage_sdf_net(const nicer_sdf_net_t &net, const LevelScales &ls,
 template <int C>
 __global__ void __launch_bounds__(SDF_BLOCK, 2)
 sdf_forward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSmemLayout lay, const float *__restrict__ X, uint32_t P,
-                   uint32_t flags, float *sdf, float *feat_fm, float *grad, float *Z, float *R, float *DYDX, float *H0) {
+                   uint32_t flags, float *sdf, float *feat_fm, float *grad, float *Z, float *R, float *DYDX, float *H0, uint32_t Pf) {
     extern __shared__ __align__(16) float smem[];
     SdfNetView nv;
     stage_sdf_net(net, ls, lay, smem, nv);
@@ -95,7 +95,7 @@ sdf_forward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSme
     const uint32_t tiles = (P + SDF_BLOCK - 1) / SDF_BLOCK;
     for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const uint32_t p = t * SDF_BLOCK + threadIdx.x;
-        if (p < P) sdf_forward_sample<C>(nv, X, p, P, flags, col, SDF_CS, sdf, feat_fm, grad, Z, R, DYDX, H0);
+        if (p < P) sdf_forward_sample<C>(nv, X, p, P, flags, col, SDF_CS, sdf, feat_fm, grad, Z, R, DYDX, H0, Pf);
     }
 }
 
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(SDF_BLOCK, 2)
 sdf_backward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSmemLayout lay, const float *__restrict__ X, uint32_t P,
                     const float *Z, const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
                     const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB, float *AB,
-                    float *TAN, float *T0) {
+                    float *TAN, float *T0, uint32_t Pf) {
     extern __shared__ __align__(16) float smem[];
     SdfNetView nv;
     stage_sdf_net(net, ls, lay, smem, nv);
@@ -115,7 +115,7 @@ sdf_backward_kernel(const nicer_sdf_net_t net, const LevelScales ls, const SdfSm
         const uint32_t p = t * SDF_BLOCK + threadIdx.x;
         if (p < P)
             sdf_backward_sample<C>(nv, X, p, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB,
-                                   TAN, T0, col, SDF_CS);
+                                   TAN, T0, col, SDF_CS, Pf);
     }
 }
 
@@ -137,10 +137,10 @@ static int check_sdf_net(const nicer_sdf_net_t *net, const char *who) {
 
 bool tc_enabled();
 int launch_sdf_only_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *F, cudaStream_t st);
-int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
+int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t Pf, uint32_t flags, float *sdf, float *feat_fm,
                           float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st);
 
-int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
+int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t Pf, const float *Z, const float *R,
                            const float *DYDX, const float *H0, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
                            float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *tan_sum, float *GY,
                            cudaStream_t st, cudaStream_t scatter_st);
@@ -177,10 +177,12 @@ static int prep_kernel(K kernel, size_t smem_bytes, const char *who) {
 
 using namespace nicer;
 
-extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf,
+extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t P_feat, uint32_t flags, float *sdf,
                                  float *feat_fm, float *grad, float *Z, float *R, float *DYDX, float *H0, void *stream) {
     if (int e = check_sdf_net(net, "nicer_sdf_forward")) return e;
     if (P == 0) return 0;
+    if (P_feat > P) NICER_FAIL(-1, "nicer_sdf_forward: P_feat (%u) > P (%u)", P_feat, P);
+    const uint32_t Pf = P_feat ? P_feat : P;
     if (!x || !sdf) NICER_FAIL(-1, "nicer_sdf_forward: x/sdf is NULL");
     const bool sdf_only = flags & NICER_SDF_ONLY;
     if (!sdf_only) {
@@ -193,7 +195,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
     if (sdf_only && tc_enabled() && net->multires == 6)
         return launch_sdf_only_tc(net, x, P, flags, sdf, H0, (cudaStream_t)stream);     // H0: optional [L*C][P] feature workspace
     if (!sdf_only && tc_enabled() && net->multires == 6)
-        return launch_sdf_forward_tc(net, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX, H0, (cudaStream_t)stream);
+        return launch_sdf_forward_tc(net, x, P, Pf, flags, sdf, feat_fm, grad, Z, R, DYDX, H0, (cudaStream_t)stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const size_t smem = (size_t)lay.total_floats * sizeof(float);
@@ -203,7 +205,7 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
 #define LAUNCH(CC)                                                                                            \
     do {                                                                                                      \
         if (int e = prep_kernel(sdf_forward_kernel<CC>, smem, "nicer_sdf_forward")) return e;                 \
-        sdf_forward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, ls, lay, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX, H0); \
+        sdf_forward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, ls, lay, x, P, flags, sdf, feat_fm, grad, Z, R, DYDX, H0, Pf); \
     } while (0)
     switch (net->grid.C) {
         case 2: LAUNCH(2); break;
@@ -215,20 +217,22 @@ extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uin
     return 0;
 }
 
-extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
+extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t P_feat, const float *Z,
                                   const float *R, const float *DYDX, const float *H0, const float *g_sdf, const float *g_feat_fm,
                                   const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
                                   float *AB, float *TAN, float *T0, float *tan_sum, float *GY, void *stream,
                                   void *scatter_stream) {
     if (int e = check_sdf_net(net, "nicer_sdf_backward")) return e;
     if (P == 0) return 0;
+    if (P_feat > P) NICER_FAIL(-1, "nicer_sdf_backward: P_feat (%u) > P (%u)", P_feat, P);
+    const uint32_t Pf = P_feat ? P_feat : P;
     if (!x || !Z || !DYDX || !ZB || !QB || !AB || !TAN || !T0)      /* grad_table may be NULL: no table gradient wanted */
         NICER_FAIL(-1, "nicer_sdf_backward: a required pointer is NULL");
     if (net->n_hidden > 1 && !R) NICER_FAIL(-1, "nicer_sdf_backward: R required for n_hidden > 1");
     if (net->n_hidden > 3) NICER_FAIL(-1, "nicer_sdf_backward: n_hidden > 3 not built");
     if (tc_enabled() && net->multires == 6 && !GY) NICER_FAIL(-1, "nicer_sdf_backward: GY workspace is NULL");
     if (tc_enabled() && net->multires == 6)
-        return launch_sdf_backward_tc(net, x, P, Z, R, DYDX, H0, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB, TAN, T0,
+        return launch_sdf_backward_tc(net, x, P, Pf, Z, R, DYDX, H0, g_sdf, g_feat_fm, g_grad, grad_x, grad_table, ZB, QB, AB, TAN, T0,
                                       tan_sum, GY, (cudaStream_t)stream, (cudaStream_t)scatter_stream);
     SdfSmemLayout lay = sdf_layout((int)net->n_hidden);
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
@@ -240,7 +244,7 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
     do {                                                                                                        \
         if (int e = prep_kernel(sdf_backward_kernel<CC>, smem, "nicer_sdf_backward")) return e;                 \
         sdf_backward_kernel<CC><<<grid, SDF_BLOCK, smem, st>>>(*net, ls, lay, x, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, \
-                                                               grad_x, grad_table, ZB, QB, AB, TAN, T0);        \
+                                                               grad_x, grad_table, ZB, QB, AB, TAN, T0, Pf);    \
     } while (0)
     switch (net->grid.C) {
         case 2: LAUNCH(2); break;

@@ -72,8 +72,9 @@ NHD void to_unit(const float x[3], float df, float u[3]) {
 template <int C>
 NHD void sdf_forward_sample(const SdfNetView &nv, const float *X, uint32_t p, uint32_t P, uint32_t flags,
                             float *col, int cs, float *sdf, float *feat_fm, float *grad, float *Z, float *R,
-                            float *DYDX, float *H0) {
-    const size_t Ps = P;
+                            float *DYDX, float *H0, uint32_t Pf = 0) {
+    // Pf: only the first Pf points have a feature row block (feat_fm is [64][Pf]); 0 = all P points
+    const size_t Ps = P, Pfs = Pf ? Pf : P;
     const int n = nv.n_hidden;
     const bool sdf_only = (flags & F_SDF_ONLY) != 0;
     const bool accumulate = (flags & F_ACCUMULATE) != 0;
@@ -142,16 +143,16 @@ NHD void sdf_forward_sample(const SdfNetView &nv, const float *X, uint32_t p, ui
         if (accumulate) sdf[p] += s; else sdf[p] = s;
     }
     if (sdf_only) return;
-    if (!(flags & F_NO_FEAT)) {
+    if (!(flags & F_NO_FEAT) && p < Pfs) {
 #pragma unroll
         for (int j = 0; j < NICER_W; ++j) acc[j] = nv.bl_feat[j];
         mv_acc64(acc, nv.WLt, col, cs, NICER_W);
         if (accumulate) {
 #pragma unroll
-            for (int j = 0; j < NICER_W; ++j) feat_fm[(size_t)j * Ps + p] += acc[j];
+            for (int j = 0; j < NICER_W; ++j) feat_fm[(size_t)j * Pfs + p] += acc[j];
         } else {
 #pragma unroll
-            for (int j = 0; j < NICER_W; ++j) feat_fm[(size_t)j * Ps + p] = acc[j];
+            for (int j = 0; j < NICER_W; ++j) feat_fm[(size_t)j * Pfs + p] = acc[j];
         }
     }
     // ---- gradient pass: q holds q_{l+1}
@@ -205,13 +206,14 @@ template <int C>
 NHD void sdf_backward_sample(const SdfNetView &nv, const float *X, uint32_t p, uint32_t P, const float *Z,
                              const float *R, const float *DYDX, const float *g_sdf, const float *g_feat_fm,
                              const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
-                             float *AB, float *TAN, float *T0, float *col, int cs) {
-    const size_t Ps = P;
+                             float *AB, float *TAN, float *T0, float *col, int cs, uint32_t Pf = 0) {
+    // Pf: g_sdf [Pf] and g_feat_fm [64][Pf] cover the first Pf points only (zero upstream gradient beyond); 0 = all P points
+    const size_t Ps = P, Pfs = Pf ? Pf : P;
     const int n = nv.n_hidden;
     float x[3] = {X[3 * (size_t)p], X[3 * (size_t)p + 1], X[3 * (size_t)p + 2]};
     float u[3];
     to_unit(x, nv.df, u);
-    const float gs = g_sdf ? g_sdf[p] : 0.f;
+    const float gs = (g_sdf && p < Pfs) ? g_sdf[p] : 0.f;
     float gg[3] = {0.f, 0.f, 0.f}, ggu[3];
     if (g_grad) { gg[0] = g_grad[3 * (size_t)p]; gg[1] = g_grad[3 * (size_t)p + 1]; gg[2] = g_grad[3 * (size_t)p + 2]; }
 #pragma unroll
@@ -278,7 +280,7 @@ NHD void sdf_backward_sample(const SdfNetView &nv, const float *X, uint32_t p, u
     // ---------------- reverse pass
     float *q = acc;
 #pragma unroll
-    for (int j = 0; j < NICER_W; ++j) q[j] = g_feat_fm ? g_feat_fm[(size_t)j * Ps + p] : 0.f;
+    for (int j = 0; j < NICER_W; ++j) q[j] = (g_feat_fm && p < Pfs) ? g_feat_fm[(size_t)j * Pfs + p] : 0.f;
     for (int k = 0; k < NICER_W; ++k) {
         const size_t o = ((size_t)(n - 1) * NICER_W + k) * Ps + p;
         const float abar = nv.wl_sdf[k] * gs + dot64(nv.WLt + k * NICER_W, q);

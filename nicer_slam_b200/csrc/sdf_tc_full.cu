@@ -245,7 +245,7 @@ int launch_grid_encode(const nicer_grid_t *g, const float *x, uint32_t P, float 
 
 // two-threads-per-point variants (sdf_tc_split.cu), selected per kernel by tc_split_mask() (1 = A, 2 = B, 4 = T, 8 = R)
 unsigned tc_split_mask();
-int launch_tcs_a(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z,
+int launch_tcs_a(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t Pf, uint32_t flags, float *sdf, float *feat_fm, float *Z,
                  float *DYDX, float *H0, cudaStream_t st);
 int launch_tcs_b(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *grad, const float *Z, float *R,
                  const float *DYDX, const float *H0, cudaStream_t st);
@@ -253,12 +253,13 @@ int launch_tcs_t(const nicer_sdf_net_t *net, const float *x, uint32_t P, const f
                  const float *H0, const float *g_grad, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *tan_sum,
                  cudaStream_t st);
 int launch_row_sum_accum(const float *rows, uint32_t n_rows, uint32_t P, float *out, cudaStream_t st);
-int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *DYDX, const float *H0,
+int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t Pf, const float *Z, const float *DYDX, const float *H0,
                  const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY,
                  cudaStream_t st);
 
-int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm,
+int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t Pf, uint32_t flags, float *sdf, float *feat_fm,
                           float *grad, float *Z, float *R, float *DYDX, float *H0, cudaStream_t st) {
+    if (Pf != P && !(tc_split_mask() & 1u)) NICER_FAIL(-1, "nicer_sdf_forward: P_feat < P needs the two-threads-per-point kernels (NICER_TC_SPLIT)");
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t pairs = div_up(div_up(P, 128), 2);
     const uint32_t grid = pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
@@ -277,7 +278,7 @@ int launch_sdf_forward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P
                    "nicer_sdf_forward(tc A)");                                                                          \
         NICER_CUDA(cudaFuncSetAttribute(sdf_forward_tc_b_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), \
                    "nicer_sdf_forward(tc B)");                                                                          \
-        if (split & 1u) { if (int e = launch_tcs_a(net, x, P, flags, sdf, feat_fm, Z, DYDX, H0, st)) return e; }          \
+        if (split & 1u) { if (int e = launch_tcs_a(net, x, P, Pf, flags, sdf, feat_fm, Z, DYDX, H0, st)) return e; }      \
         else sdf_forward_tc_a_kernel<CC><<<grid, TCF_THREADS, smem_a, st>>>(*net, ls, pa, x, P, flags, sdf, feat_fm, Z, DYDX, H0); \
         if (split & 2u) { if (int e = launch_tcs_b(net, x, P, flags, grad, Z, R, DYDX, pe_h0, st)) return e; }                     \
         else sdf_forward_tc_b_kernel<CC><<<grid, TCF_THREADS, smem_b, st>>>(*net, ls, pb, x, P, flags, grad, Z, R, DYDX);   \
@@ -542,11 +543,12 @@ sdf_backward_tc_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
 int launch_grid_scatter(const nicer_grid_t *g, const float *x, uint32_t P, const float *GY1, const float *GY2,
                         const float *g_grad, float *grad_table, cudaStream_t st);
 
-int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *R,
+int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t Pf, const float *Z, const float *R,
                            const float *DYDX, const float *H0, const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x,
                            float *grad_table, float *ZB, float *QB, float *AB, float *TAN, float *T0, float *tan_sum, float *GY,
                            cudaStream_t st, cudaStream_t scatter_st) {
     const unsigned split = tc_split_mask();
+    if (Pf != P && !(split & 8u)) NICER_FAIL(-1, "nicer_sdf_backward: P_feat < P needs the two-threads-per-point kernels (NICER_TC_SPLIT)");
     static const bool pe_reload = [] { const char *e = getenv("NICER_PE_RELOAD"); return !(e && e[0] == '0'); }();
     const float *pe_h0 = pe_reload ? H0 : nullptr;
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
@@ -562,7 +564,7 @@ int launch_sdf_backward_tc(const nicer_sdf_net_t *net, const float *x, uint32_t 
                    "nicer_sdf_backward(tc R)");                                                                          \
         if (split & 4u) { if (int e = launch_tcs_t(net, x, P, Z, R, DYDX, pe_h0, g_grad, ZB, QB, AB, TAN, T0, tan_sum, st)) return e; } \
         else sdf_backward_tc_t_kernel<CC><<<grid, TCF_THREADS, smem_t, st>>>(*net, ls, pt, x, P, Z, R, DYDX, g_grad, ZB, QB, AB, TAN, T0); \
-        if (split & 8u) { if (int e = launch_tcs_r(net, x, P, Z, DYDX, pe_h0, g_sdf, g_feat_fm, g_grad, grad_x, ZB, QB, GY, st)) return e; } \
+        if (split & 8u) { if (int e = launch_tcs_r(net, x, P, Pf, Z, DYDX, pe_h0, g_sdf, g_feat_fm, g_grad, grad_x, ZB, QB, GY, st)) return e; } \
         else sdf_backward_tc_r_kernel<CC><<<grid, TCF_THREADS, smem_r, st>>>(*net, ls, pr, x, P, Z, DYDX, g_sdf, g_feat_fm, g_grad, grad_x, \
                                                                         ZB, QB, GY);                                     \
     } while (0)

@@ -30,8 +30,10 @@ __device__ __forceinline__ void mat_gemm2(Tile &t, const TcfPlan &pl, int i, flo
 template <int C>
 __global__ void __launch_bounds__(TCS_THREADS, 1)
 sdf_forward_tcs_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
-                         uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z, float *DYDX, float *H0) {
+                         uint32_t P, uint32_t Pf, uint32_t flags, float *sdf, float *feat_fm, float *Z, float *DYDX, float *H0) {
     // H0 != NULL: its grid rows (and DYDX) were already written by grid_encode_kernel; this kernel adds the x / PE rows
+    // Pf <= P: only the first Pf points get features (feat_fm is [64][Pf]); tiles beyond skip the feature head (eikonal points
+    // batched behind the main-pass points)
     extern __shared__ __align__(16) float smem[];
     __shared__ TcsShared sh;
     LevelInfo *lv;
@@ -118,22 +120,23 @@ sdf_forward_tcs_a_kernel(const nicer_sdf_net_t net, const LevelScales ls, const 
             st_half(t, c0, v);
         }
         // ---------------- sdf = b + w_n . a_n: upper half of the dot product handed over through shared memory
+        const bool tile_feat = want_feat && tt * 128u < Pf;                   // tile-uniform
         if (h == 1) sh.xch[tile][lane][0] = s_part;
-        if (want_feat) mat_issue2(t, pl, n, smem); else tile_sync2(t);       // both contain the tile barrier
+        if (tile_feat) mat_issue2(t, pl, n, smem); else tile_sync2(t);        // both contain the tile barrier
         if (h == 0 && valid) {
             const float s_out = s_part + sh.xch[tile][lane][0];
             if (accumulate) sdf[p] += s_out; else sdf[p] = s_out;
         }
         // ---------------- feature head
-        if (want_feat) {
+        if (tile_feat) {
             gemm_wait(t);
             const float *bias = smem + pl.bias[n] + c0 * 8;
             float v[32];
             ld_half(t, c0, v);
-            if (valid) {
+            if (valid && p < Pf) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    float *dst = feat_fm + (size_t)(c0 * 8 + i) * Ps + p;
+                    float *dst = feat_fm + (size_t)(c0 * 8 + i) * Pf + p;
                     const float f = v[i] + bias[i];
                     if (accumulate) *dst += f; else *dst = f;
                 }
@@ -423,8 +426,9 @@ sdf_backward_tcs_t_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
 template <int C>
 __global__ void __launch_bounds__(TCS_THREADS, 1)
 sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const TcfPlan pl, const float *__restrict__ X,
-                          uint32_t P, const float *Z, const float *DYDX, const float *__restrict__ H0, const float *g_sdf,
+                          uint32_t P, uint32_t Pf, const float *Z, const float *DYDX, const float *__restrict__ H0, const float *g_sdf,
                           const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY) {
+    // Pf <= P: g_sdf [Pf] and g_feat_fm [64][Pf] cover the first Pf points; the upstream gradient of the others is zero
     extern __shared__ __align__(16) float smem[];
     __shared__ TcsShared sh;
     LevelInfo *lv;
@@ -440,12 +444,13 @@ sdf_backward_tcs_r_kernel(const nicer_sdf_net_t net, const LevelScales ls, const
         uint32_t p = tt * 128u + lane;
         const bool valid = p < P;
         if (!valid) p = P - 1;
-        const float gs = g_sdf ? g_sdf[p] : 0.f;
+        const bool has_up = p < Pf;
+        const float gs = (g_sdf && has_up) ? g_sdf[p] : 0.f;
         // ---- A = g_feat -> abar_n' = (W_n[1:])^T g_feat
         {
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = g_feat_fm ? g_feat_fm[(size_t)(c0 * 8 + i) * Ps + p] : 0.f;
+            for (int i = 0; i < 32; ++i) v[i] = (g_feat_fm && has_up) ? g_feat_fm[(size_t)(c0 * 8 + i) * Pf + p] : 0.f;
             st_half(t, c0, v);
         }
         mat_issue2(t, pl, n, smem);
@@ -610,13 +615,13 @@ static uint32_t tcs_grid(uint32_t P) {
     return pairs < (uint32_t)num_sms() ? pairs : (uint32_t)num_sms();
 }
 
-int launch_tcs_a(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf, float *feat_fm, float *Z,
+int launch_tcs_a(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t Pf, uint32_t flags, float *sdf, float *feat_fm, float *Z,
                  float *DYDX, float *H0, cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t grid = tcs_grid(P);
     const TcfPlan pl = plan_a(net);
     const size_t smem = (size_t)pl.total_floats * sizeof(float);
-    TCS_DISPATCH(sdf_forward_tcs_a_kernel, smem, "nicer_sdf_forward(tcs A)", *net, ls, pl, x, P, flags, sdf, feat_fm, Z, DYDX, H0);
+    TCS_DISPATCH(sdf_forward_tcs_a_kernel, smem, "nicer_sdf_forward(tcs A)", *net, ls, pl, x, P, Pf, flags, sdf, feat_fm, Z, DYDX, H0);
     return 0;
 }
 
@@ -642,14 +647,14 @@ int launch_tcs_t(const nicer_sdf_net_t *net, const float *x, uint32_t P, const f
     return 0;
 }
 
-int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z, const float *DYDX, const float *H0,
+int launch_tcs_r(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t Pf, const float *Z, const float *DYDX, const float *H0,
                  const float *g_sdf, const float *g_feat_fm, const float *g_grad, float *grad_x, float *ZB, const float *QB, float *GY,
                  cudaStream_t st) {
     const LevelScales ls = host_level_scales(net->grid.L, net->grid.S, net->grid.H);
     const uint32_t grid = tcs_grid(P);
     const TcfPlan pl = plan_r(net);
     const size_t smem = (size_t)pl.total_floats * sizeof(float);
-    TCS_DISPATCH(sdf_backward_tcs_r_kernel, smem, "nicer_sdf_backward(tcs R)", *net, ls, pl, x, P, Z, DYDX, H0, g_sdf, g_feat_fm, g_grad,
+    TCS_DISPATCH(sdf_backward_tcs_r_kernel, smem, "nicer_sdf_backward(tcs R)", *net, ls, pl, x, P, Pf, Z, DYDX, H0, g_sdf, g_feat_fm, g_grad,
                  grad_x, ZB, QB, GY);
     return 0;
 }

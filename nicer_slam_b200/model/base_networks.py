@@ -113,6 +113,20 @@ class ImplicitNetworkGrid_COMBINE(nn.Module):
         f_sdf, f_feat, f_grad = self.fine.get_outputs(x, c_feature_vectors=c_feat)
         return c_sdf + f_sdf, c_feat + f_feat, c_grad + f_grad
 
+    def can_batch_gradient(self, stage="fine"):
+        """True when get_outputs_and_gradient runs both point sets through one set of kernel launches."""
+        nets = [self.coarse] if stage == "coarse" else [self.coarse, self.fine]
+        return all(n.fused for n in nets) and not self.fine.concat_coarse_feature
+
+    def get_outputs_and_gradient(self, x, x_grad_only, stage="fine"):
+        """get_outputs(x) and gradient(x_grad_only) (the eikonal samples, network.py:313-336) in one pass per network:
+        returns (sdf, feature, gradient) of x and the gradient of x_grad_only."""
+        if stage == "coarse":
+            return self.coarse.get_outputs_and_gradient(x, x_grad_only)
+        c = self.coarse.get_outputs_and_gradient(x, x_grad_only)
+        f = self.fine.get_outputs_and_gradient(x, x_grad_only)
+        return tuple(a + b for a, b in zip(c, f))
+
     def gradient(self, x, stage="fine"):
         if stage == "coarse":
             return self.coarse.gradient(x)
@@ -193,6 +207,12 @@ class ImplicitNetworkGrid(nn.Module):
     def _fused_outputs(self, x, want_feat):
         meta, table, offsets, wb = self.fused_args()
         return ops.SdfNetFn.apply(x, table, offsets, meta, want_feat, *wb)
+
+    def get_outputs_and_gradient(self, x, x_grad_only):
+        if self.fused:
+            meta, table, offsets, wb = self.fused_args()
+            return ops.SdfNetPairFn.apply(x, x_grad_only, table, offsets, meta, True, *wb)
+        return (*self.get_outputs(x), self.gradient(x_grad_only))
 
     # ---- layer-by-layer path (general option set)
     def forward(self, input, c_feature_vectors=None):

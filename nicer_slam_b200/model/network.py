@@ -20,6 +20,10 @@ from .base_networks import ImplicitNetworkGrid_COMBINE, RenderingNetwork, detach
 from .density import GridPredefineDensity, LaplaceDensity
 from .ray_sampler import DeviceRng, ImportantSampler
 
+import os as _os
+# NICER_EIK_BATCHED=0: the eikonal samples go through the SDF networks in their own pass, as in the reference
+_EIK_BATCHED = _os.environ.get("NICER_EIK_BATCHED", "1") != "0"
+
 
 class SLAMNetwork(nn.Module):
     def __init__(self, conf, dataset=None, n_images=2000):
@@ -134,7 +138,24 @@ class SLAMNetwork(nn.Module):
         if mode == "mapping":
             self.update_voxels(points_flat.detach())
 
-        sdf, feature_vectors, gradients = self.implicit_network.get_outputs(points_flat, stage=stage)
+        # eikonal samples: 10 uniform points per ray + one near-surface point per ray, each with a jittered neighbour
+        # (network.py:313-336).  Drawn here -- the main pass draws no random numbers, so the order of the draws is the reference's --
+        # so that they can ride behind the main-pass points through the SDF networks in one set of launches.
+        eik = None
+        want_eik = self.training and ("vis" not in mode) and ("mapping" in mode)
+        if want_eik:
+            n_eik = batch_size * num_pixels
+            dev = points_flat.device
+            eik = self.rng.eik_uniform(n_eik * 10, self.scene_bounding_sphere, dev)
+            with torch.no_grad():
+                near_surface = (cam_loc.unsqueeze(1) + z_samples_eik.unsqueeze(2) * ray_dirs.unsqueeze(1)).reshape(-1, 3)
+            eik = torch.cat([eik, near_surface], 0)
+            eik = torch.cat([eik, eik + (self.rng.eik_jitter(eik) - 0.5) * 0.01], 0)
+        grad_theta = None
+        if want_eik and _EIK_BATCHED and self.implicit_network.can_batch_gradient(stage):
+            sdf, feature_vectors, gradients, grad_theta = self.implicit_network.get_outputs_and_gradient(points_flat, eik, stage=stage)
+        else:
+            sdf, feature_vectors, gradients = self.implicit_network.get_outputs(points_flat, stage=stage)
         rgb_flat = self.rendering_network(points_flat, gradients, dirs_flat, feature_vectors, indices,
                                           color_stage=color_stage)
         rgb = rgb_flat.reshape(-1, N_samples, 3)
@@ -179,17 +200,9 @@ class SLAMNetwork(nn.Module):
             "scene_bounding_sphere": self.scene_bounding_sphere,
         })
 
-        if self.training and ("vis" not in mode) and ("mapping" in mode):
-            # eikonal samples: 10 uniform points per ray + one near-surface point per ray, each with a jittered
-            # neighbour (network.py:313-336)
-            n_eik = batch_size * num_pixels
-            dev = points_flat.device
-            eik = self.rng.eik_uniform(n_eik * 10, self.scene_bounding_sphere, dev)
-            with torch.no_grad():
-                near_surface = (cam_loc.unsqueeze(1) + z_samples_eik.unsqueeze(2) * ray_dirs.unsqueeze(1)).reshape(-1, 3)
-            eik = torch.cat([eik, near_surface], 0)
-            eik = torch.cat([eik, eik + (self.rng.eik_jitter(eik) - 0.5) * 0.01], 0)
-            grad_theta = self.implicit_network.gradient(eik, stage=stage)
+        if want_eik:
+            if grad_theta is None:
+                grad_theta = self.implicit_network.gradient(eik, stage=stage)
             half = grad_theta.shape[0] // 2
             output["grad_theta"], output["grad_theta_nei"] = grad_theta[:half], grad_theta[half:]
 

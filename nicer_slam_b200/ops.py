@@ -197,6 +197,14 @@ def outer_accum(A, B, Cmat, bias=None, col0=0):
                                   ptr(bias) if bias is not None else None, stream()), "nicer_outer_accum")
 
 
+def _rows(t, name):
+    """[rows, P] operand of a contraction: rows may be strided (a column range of a wider buffer), samples must be contiguous."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"{name} must be a [rows, samples] tensor with contiguous samples")
+    _lib.require(t[0], torch.float32, name)      # device / dtype guard on one (contiguous) row
+    return t
+
+
 class OuterAccumBatch:
     """Collects the weight / bias gradient contractions of one network backward (all over the same P samples) and issues
     them through nicer_outer_accum_batch: one kernel launch per 8 jobs instead of one per job."""
@@ -209,8 +217,8 @@ class OuterAccumBatch:
             outer_accum(A, B, Cmat, bias, col0)
             return
         j = OaJobT()
-        j.A, j.lda, j.M = _lib.require(A, torch.float32, "A").data_ptr(), A.stride(0), A.shape[0]
-        j.B, j.ldb, j.N = _lib.require(B, torch.float32, "B").data_ptr(), B.stride(0), B.shape[0]
+        j.A, j.lda, j.M = _rows(A, "A").data_ptr(), A.stride(0), A.shape[0]
+        j.B, j.ldb, j.N = _rows(B, "B").data_ptr(), B.stride(0), B.shape[0]
         j.C, j.ldc = _lib.require(Cmat, torch.float32, "C").data_ptr() + 4 * col0, Cmat.stride(0)
         j.bias = _lib.require(bias, torch.float32, "bias").data_ptr() if bias is not None else None
         self.jobs.append(j)
@@ -271,90 +279,147 @@ class WeightNormFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------- SDF network
+def _sdf_forward_impl(ctx, x, Pf, table, offsets, meta, want_feat, wb):
+    """x [P,3]: all points; the first Pf of them carry features (Pf == P for the plain call).  Returns (sdf [P], feat_fm [64,Pf] |
+    None, grad [P,3]) and saves what the backward needs on ctx."""
+    wb = tuple(_c(t.detach()) for t in wb)
+    table_d = table.detach()
+    P = x.shape[0]
+    n = meta.n_hidden
+    dev = x.device
+    sdf = torch.empty(P, device=dev)
+    feat_fm = torch.empty(HIDDEN, Pf, device=dev) if want_feat else None
+    grad = torch.empty(P, 3, device=dev)
+    Z = torch.empty(n * HIDDEN, P, device=dev)
+    R = torch.empty((n - 1) * HIDDEN, P, device=dev) if n > 1 else None
+    DYDX = torch.empty(meta.grid.L * 3 * meta.grid.C, P, device=dev)
+    H0 = torch.empty(meta.d_in, P, device=dev)      # network input, kept for the layer-0 weight gradient
+    net = _sdf_struct(meta, table_d, offsets, wb)
+    flags = 0 if want_feat else F_NO_FEAT
+    check(lib().nicer_sdf_forward(C.byref(net), ptr(x), P, Pf, flags, ptr(sdf), ptr(feat_fm), ptr(grad), ptr(Z),
+                                  ptr(R), ptr(DYDX), ptr(H0), stream()), "nicer_sdf_forward")
+    ctx.meta, ctx.want_feat, ctx.Pf = meta, want_feat, Pf
+    ctx.save_for_backward(x, table_d, offsets, Z, R, DYDX, H0, *wb)
+    ctx.set_materialize_grads(False)
+    return sdf, feat_fm, grad
+
+
+def _sdf_backward_impl(ctx, g_sdf, g_feat, gg, need_x, need_table, need_w):
+    """g_sdf [Pf,1] | None, g_feat [Pf,F] | None (upstream gradients of the first Pf points), gg [P,3] | None.
+    Returns (grad_x [P,3] | None, grad_table | None, [dW_0, db_0, ...] | None)."""
+    x, table, offsets, Z, R, DYDX, H0, *wb = ctx.saved_tensors
+    meta, Pf = ctx.meta, ctx.Pf
+    n, P, dev = meta.n_hidden, x.shape[0], x.device
+    nfeat = meta.d_out - 1
+    gs = _c(g_sdf.reshape(Pf)) if g_sdf is not None else None
+    gf = None
+    if g_feat is not None and ctx.want_feat:
+        gf = _fm(g_feat)
+        if nfeat < HIDDEN:
+            pad = torch.zeros(HIDDEN, Pf, device=dev)
+            pad[:nfeat] = gf
+            gf = pad
+    grad_x = torch.zeros(P, 3, device=dev) if need_x else None
+    # pose-only tracking (detached parameters): no table scatter, no weight-gradient contractions
+    grad_table = torch.zeros_like(table) if need_table else None
+    ZB = torch.empty(n * HIDDEN, P, device=dev)
+    QB, AB, TAN = torch.empty_like(ZB), torch.empty_like(ZB), torch.empty_like(ZB)
+    T0 = torch.empty(meta.d_in, P, device=dev)
+    GY = torch.empty(2 * meta.grid.L * meta.grid.C, P, device=dev)     # MLP-backward -> grid-scatter hand-over
+    net = _sdf_struct(meta, table, offsets, wb)
+    side = _scatter_stream(dev)
+    zeros = _zeros_like_many(list(wb)) if need_w else None        # dW_0, db_0, dW_1, ... in one buffer
+    # the tangent kernel adds sum_p tan_n (second-order part of the sdf row of dW_n) straight into dW_n[0, :]
+    tan_sum = zeros[2 * n][0] if need_w else None
+    check(lib().nicer_sdf_backward(C.byref(net), ptr(x), P, Pf, ptr(Z), ptr(R), ptr(DYDX), ptr(H0), ptr(gs), ptr(gf), ptr(gg),
+                                   ptr(grad_x), ptr(grad_table), ptr(ZB), ptr(QB), ptr(AB), ptr(TAN),
+                                   ptr(T0), ptr(tan_sum), ptr(GY), stream(), _sptr(side)), "nicer_sdf_backward")
+    if not need_w:
+        _join(side, None, defer=False)
+        return grad_x, grad_table, None
+    grads = []
+    oa = OuterAccumBatch()
+    oa_f = OuterAccumBatch()        # contractions over the first Pf points only (upstream sdf / feature gradients)
+    for l in range(n + 1):
+        dW, db = zeros[2 * l], zeros[2 * l + 1]
+        if l == 0:
+            oa.add(ZB[:HIDDEN], H0, dW, db)
+            oa.add(QB[:HIDDEN], T0, dW)
+        elif l < n:
+            oa.add(ZB[l * HIDDEN:(l + 1) * HIDDEN], AB[(l - 1) * HIDDEN:l * HIDDEN], dW, db)
+            oa.add(QB[l * HIDDEN:(l + 1) * HIDDEN], TAN[(l - 1) * HIDDEN:l * HIDDEN], dW)
+        else:
+            a_n = AB[(n - 1) * HIDDEN:, :Pf]        # rows of stride P, the first Pf samples of each
+            if gs is not None:
+                oa_f.add(gs.view(1, Pf), a_n, dW[:1], db[:1])
+            if gf is not None and nfeat > 0:
+                oa_f.add(gf[:nfeat], a_n, dW[1:], db[1:])
+        grads += [dW, db]
+    oa.flush()
+    oa_f.flush()
+    _join(side, None, defer=False)       # the scatter overlapped with the weight-gradient GEMMs above
+    return grad_x, grad_table, grads
+
+
 class SdfNetFn(torch.autograd.Function):
     """(x, table, W0,b0,...,Wn,bn) -> (sdf [P,1], feat [P,F] (view of [F,P]), grad [P,3])."""
 
     @staticmethod
     def forward(ctx, x, table, offsets, meta, want_feat, *wb):
         x = _c(x.detach())
-        wb = tuple(_c(t.detach()) for t in wb)
-        table_d = table.detach()
         P = x.shape[0]
-        n = meta.n_hidden
-        dev = x.device
-        sdf = torch.empty(P, device=dev)
-        feat_fm = torch.empty(HIDDEN, P, device=dev) if want_feat else None
-        grad = torch.empty(P, 3, device=dev)
-        Z = torch.empty(n * HIDDEN, P, device=dev)
-        R = torch.empty((n - 1) * HIDDEN, P, device=dev) if n > 1 else None
-        DYDX = torch.empty(meta.grid.L * 3 * meta.grid.C, P, device=dev)
-        H0 = torch.empty(meta.d_in, P, device=dev)      # network input, kept for the layer-0 weight gradient
-        net = _sdf_struct(meta, table_d, offsets, wb)
-        flags = 0 if want_feat else F_NO_FEAT
-        check(lib().nicer_sdf_forward(C.byref(net), ptr(x), P, flags, ptr(sdf), ptr(feat_fm), ptr(grad), ptr(Z),
-                                      ptr(R), ptr(DYDX), ptr(H0), stream()), "nicer_sdf_forward")
-        ctx.meta, ctx.want_feat = meta, want_feat
-        ctx.save_for_backward(x, table_d, offsets, Z, R, DYDX, H0, *wb)
-        ctx.set_materialize_grads(False)
+        sdf, feat_fm, grad = _sdf_forward_impl(ctx, x, P, table, offsets, meta, want_feat, wb)
         nfeat = meta.d_out - 1
-        feat = feat_fm[:nfeat].t() if want_feat else torch.zeros(P, 0, device=dev)
+        feat = feat_fm[:nfeat].t() if want_feat else torch.zeros(P, 0, device=x.device)
         return sdf.view(P, 1), feat, grad
 
     @staticmethod
     def backward(ctx, g_sdf, g_feat, g_grad):
-        x, table, offsets, Z, R, DYDX, H0, *wb = ctx.saved_tensors
-        meta = ctx.meta
-        n, P, dev = meta.n_hidden, x.shape[0], x.device
-        nfeat = meta.d_out - 1
-        gs = _c(g_sdf.reshape(P)) if g_sdf is not None else None
-        gf = None
-        if g_feat is not None and ctx.want_feat:
-            gf = _fm(g_feat)
-            if nfeat < HIDDEN:
-                pad = torch.zeros(HIDDEN, P, device=dev)
-                pad[:nfeat] = gf
-                gf = pad
+        n_wb = len(ctx.saved_tensors) - 7
         gg = _c(g_grad) if g_grad is not None else None
-        grad_x = torch.zeros(P, 3, device=dev) if ctx.needs_input_grad[0] else None
-        # pose-only tracking (detached parameters): no table scatter, no weight-gradient contractions
-        need_table, need_w = ctx.needs_input_grad[1], any(ctx.needs_input_grad[5:])
-        grad_table = torch.zeros_like(table) if need_table else None
-        ZB = torch.empty(n * HIDDEN, P, device=dev)
-        QB, AB, TAN = torch.empty_like(ZB), torch.empty_like(ZB), torch.empty_like(ZB)
-        T0 = torch.empty(meta.d_in, P, device=dev)
-        GY = torch.empty(2 * meta.grid.L * meta.grid.C, P, device=dev)     # MLP-backward -> grid-scatter hand-over
-        net = _sdf_struct(meta, table, offsets, wb)
-        side = _scatter_stream(dev)
-        zeros = _zeros_like_many(list(wb)) if need_w else None        # dW_0, db_0, dW_1, ... in one buffer
-        # the tangent kernel adds sum_p tan_n (second-order part of the sdf row of dW_n) straight into dW_n[0, :]
-        tan_sum = zeros[2 * n][0] if need_w else None
-        check(lib().nicer_sdf_backward(C.byref(net), ptr(x), P, ptr(Z), ptr(R), ptr(DYDX), ptr(H0), ptr(gs), ptr(gf), ptr(gg),
-                                       ptr(grad_x), ptr(grad_table), ptr(ZB), ptr(QB), ptr(AB), ptr(TAN),
-                                       ptr(T0), ptr(tan_sum), ptr(GY), stream(), _sptr(side)), "nicer_sdf_backward")
-        if not need_w:
-            _join(side, None, defer=False)
-            return (grad_x, grad_table, None, None, None, *([None] * len(wb)))
-        grads = []
-        oa = OuterAccumBatch()
-        for l in range(n + 1):
-            W = wb[2 * l]
-            dW, db = zeros[2 * l], zeros[2 * l + 1]
-            if l == 0:
-                oa.add(ZB[:HIDDEN], H0, dW, db)
-                oa.add(QB[:HIDDEN], T0, dW)
-            elif l < n:
-                oa.add(ZB[l * HIDDEN:(l + 1) * HIDDEN], AB[(l - 1) * HIDDEN:l * HIDDEN], dW, db)
-                oa.add(QB[l * HIDDEN:(l + 1) * HIDDEN], TAN[(l - 1) * HIDDEN:l * HIDDEN], dW)
+        grad_x, grad_table, grads = _sdf_backward_impl(ctx, g_sdf, g_feat, gg, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                                       any(ctx.needs_input_grad[5:]))
+        return (grad_x, grad_table, None, None, None, *(grads if grads is not None else [None] * n_wb))
+
+
+class SdfNetPairFn(torch.autograd.Function):
+    """(x [P1,3], x2 [P2,3], table, ...) -> (sdf [P1,1], feat [P1,F], grad [P1,3], grad2 [P2,3]): the main-pass points and a
+    second set that only needs d sdf/dx (the eikonal samples, network.py:313-336) in ONE set of launches -- 13 instead of 14 waves of
+    128-point tile pairs at the demo_2 shape, one staging of the weights, one weight-gradient batch, no second accumulation of
+    every parameter gradient.  The second set takes no part in the feature head (nicer_sdf_forward's P_feat)."""
+
+    @staticmethod
+    def forward(ctx, x, x2, table, offsets, meta, want_feat, *wb):
+        P1, P2 = x.shape[0], x2.shape[0]
+        xa = torch.cat([x.detach(), x2.detach()], 0)
+        sdf, feat_fm, grad = _sdf_forward_impl(ctx, xa, P1, table, offsets, meta, want_feat, wb)
+        ctx.P1 = P1
+        nfeat = meta.d_out - 1
+        feat = feat_fm[:nfeat].t() if want_feat else torch.zeros(P1, 0, device=xa.device)
+        return sdf[:P1].view(P1, 1), feat, grad[:P1], grad[P1:]
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_feat, g_grad, g_grad2):
+        n_wb = len(ctx.saved_tensors) - 7
+        x = ctx.saved_tensors[0]
+        P, P1 = x.shape[0], ctx.P1
+        gg = None
+        if g_grad is not None or g_grad2 is not None:
+            gg = torch.empty(P, 3, device=x.device)
+            if g_grad is not None:
+                gg[:P1] = g_grad
             else:
-                a_n = AB[(n - 1) * HIDDEN:]
-                if gs is not None:
-                    oa.add(gs.view(1, P), a_n, dW[:1], db[:1])
-                if gf is not None and nfeat > 0:
-                    oa.add(gf[:nfeat], a_n, dW[1:], db[1:])
-            grads += [dW, db]
-        oa.flush()
-        _join(side, None, defer=False)       # the scatter overlapped with the weight-gradient GEMMs above
-        return (grad_x, grad_table, None, None, None, *grads)
+                gg[:P1].zero_()
+            if g_grad2 is not None:
+                gg[P1:] = g_grad2
+            else:
+                gg[P1:].zero_()
+        need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        grad_x, grad_table, grads = _sdf_backward_impl(ctx, g_sdf, g_feat, gg, need_x, ctx.needs_input_grad[2],
+                                                       any(ctx.needs_input_grad[6:]))
+        gx = grad_x[:P1] if (grad_x is not None and ctx.needs_input_grad[0]) else None
+        gx2 = grad_x[P1:] if (grad_x is not None and ctx.needs_input_grad[1]) else None
+        return (gx, gx2, grad_table, None, None, None, *(grads if grads is not None else [None] * n_wb))
 
 
 def sdf_values(x, nets, out=None):
@@ -370,7 +435,7 @@ def sdf_values(x, nets, out=None):
         wb = tuple(_c(t.detach()) for t in wb)
         net = _sdf_struct(meta, table.detach(), offsets, wb)
         flags = F_SDF_ONLY | (F_ACCUMULATE if i > 0 else 0)
-        check(lib().nicer_sdf_forward(C.byref(net), ptr(x), P, flags, ptr(sdf), None, None, None, None, None,
+        check(lib().nicer_sdf_forward(C.byref(net), ptr(x), P, 0, flags, ptr(sdf), None, None, None, None, None,
                                       ptr(feat_ws), stream()), "nicer_sdf_forward")
     return sdf.view(P, 1)
 

@@ -91,16 +91,16 @@ struct HostColor {
         default: return fail("bad C"); \
     }
 
-extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t flags, float *sdf,
+extern "C" int nicer_sdf_forward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t P_feat, uint32_t flags, float *sdf,
                                  float *feat_fm, float *grad, float *Z, float *R, float *DYDX, float *H0, void *) {
     HostSdf h(*net);
     float col[COL_ROWS];
     for (uint32_t p = 0; p < P; ++p)
-        DISPATCH_C(net->grid.C, (sdf_forward_sample<CC>(h.nv, x, p, P, flags, col, 1, sdf, feat_fm, grad, Z, R, DYDX, H0)));
+        DISPATCH_C(net->grid.C, (sdf_forward_sample<CC>(h.nv, x, p, P, flags, col, 1, sdf, feat_fm, grad, Z, R, DYDX, H0, P_feat)));
     return 0;
 }
 
-extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, const float *Z,
+extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, uint32_t P, uint32_t P_feat, const float *Z,
                                   const float *R, const float *DYDX, const float * /*H0*/, const float *g_sdf, const float *g_feat_fm,
                                   const float *g_grad, float *grad_x, float *grad_table, float *ZB, float *QB,
                                   float *AB, float *TAN, float *T0, float *tan_sum, float * /*GY*/, void *, void *) {
@@ -108,7 +108,7 @@ extern "C" int nicer_sdf_backward(const nicer_sdf_net_t *net, const float *x, ui
     float col[COL_ROWS];
     for (uint32_t p = 0; p < P; ++p)
         DISPATCH_C(net->grid.C, (sdf_backward_sample<CC>(h.nv, x, p, P, Z, R, DYDX, g_sdf, g_feat_fm, g_grad, grad_x,
-                                                         grad_table, ZB, QB, AB, TAN, T0, col, 1)));
+                                                         grad_table, ZB, QB, AB, TAN, T0, col, 1, P_feat)));
     if (tan_sum) {
         const size_t row0 = (size_t)(net->n_hidden - 1) * 64;
         for (int j = 0; j < 64; ++j) {
