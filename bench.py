@@ -613,13 +613,17 @@ def kernel_breakdown(step, dev, P, S):
     view = torch.randn(P, 3, device=dev)
     stream = torch.cuda.current_stream()
 
-    def timed(fn0, n=5, reps=3):
+    def timed(fn0, n=5, reps=5):
         """median over `reps` of (n back-to-back calls between two events) / n: launch latency is amortised over the queue,
-        and a one-off allocator / lazy-init hiccup cannot leak into a per-kernel figure"""
+        and a one-off allocator / lazy-init hiccup cannot leak into a per-kernel figure.  Three untimed calls first: the caching
+        allocator needs a few rounds before the 1 GB gradient buffer and the 100-200 MB workspaces stop splitting each other's
+        cached blocks (one run showed a 4x slower color pass from cudaMalloc inside the timed calls)"""
         def fn():
             m.zero_grad(set_to_none=True)      # do not time gradient accumulation into 1 GB .grad buffers
             fn0()
-        fn(); torch.cuda.synchronize()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
