@@ -52,6 +52,47 @@ def test_sdf_net_first_and_second_order(hidden, L, C, logmap):
         assert rel(a, b) < 1e-4
 
 
+def test_sdf_net_second_point_set_equals_two_calls():
+    """ops.SdfNetPairFn (main-pass points + a second set that only needs d sdf/dx, batched through one set of kernel calls with
+    P_feat = the size of the first set) == SdfNetFn on the first set + SdfNetFn(want_feat=False) on the second: outputs and all
+    gradients, with the oracle as the common reference for the second set's gradient."""
+    from nicer_slam_b200 import ops
+    torch.manual_seed(3)
+    L, C, hidden = 4, 4, [64, 64, 64]
+    spec = ro.GridSpec(L, C, 4, 16, 10)
+    net = ro.make_sdf_net(spec, hidden, 64, seed=5, table_scale=0.3)
+    P1, P2 = 150, 70
+    xa, xb = torch.rand(P1, 3) * 2.1 - 1.05, torch.rand(P2, 3) * 2.0 - 1.0
+    wS, wF, wG, wG2 = torch.randn(P1, 1), torch.randn(P1, 64), torch.randn(P1, 3), torch.randn(P2, 3)
+    meta = ops.SdfMeta(ops.GridMeta(L, C, 4, float(np.log2(spec.pls)), 1.0), 6, len(hidden), 65)
+
+    def leaves():
+        tab = net["table"].detach().clone().requires_grad_(True)
+        vgb = [[t.detach().clone().requires_grad_(True) for t in l] for l in net["layers"]]
+        return tab, vgb
+
+    with emulated_library():
+        tab, vgb = leaves()
+        x1, x2 = xa.clone().requires_grad_(True), xb.clone().requires_grad_(True)
+        s, f, g, g2 = ops.SdfNetPairFn.apply(x1, x2, tab, spec.offsets, meta, True, *_wb(vgb))
+        got = torch.autograd.grad((s * wS).sum() + (f * wF).sum() + (g * wG).sum() + (g2 * wG2).sum(),
+                                  [x1, x2, tab] + [t for l in vgb for t in l])
+        tab_r, vgb_r = leaves()
+        y1, y2 = xa.clone().requires_grad_(True), xb.clone().requires_grad_(True)
+        sr, fr, gr = ops.SdfNetFn.apply(y1, tab_r, spec.offsets, meta, True, *_wb(vgb_r))
+        _, _, g2r = ops.SdfNetFn.apply(y2, tab_r, spec.offsets, meta, False, *_wb(vgb_r))
+        want = torch.autograd.grad((sr * wS).sum() + (fr * wF).sum() + (gr * wG).sum() + (g2r * wG2).sum(),
+                                   [y1, y2, tab_r] + [t for l in vgb_r for t in l])
+    assert torch.equal(s, sr) and torch.equal(f, fr) and torch.equal(g, gr) and torch.equal(g2, g2r)
+    assert f.shape == (P1, 64) and g2.shape == (P2, 3)
+    for a, b in zip(got, want):
+        assert rel(a, b) < 2e-6, rel(a, b)
+    # and against the oracle for the second set
+    xo = xb.clone().requires_grad_(True)
+    _, _, go = ro.sdf_net_outputs(xo, net)
+    assert rel(g2, go) < 5e-6
+
+
 @pytest.mark.parametrize("stage", ["highfreq", "base"])
 def test_color_net(stage):
     torch.manual_seed(1)
