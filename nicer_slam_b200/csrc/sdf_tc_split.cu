@@ -8,11 +8,16 @@
 // part (features, d feat/dx rows, grid-gradient hand-over), h = 1 the x / positional-encoding part.
 //
 // Why: with one thread per point the kernels held 64-wide register arrays (254-255 registers, 8 warps per SM) and ncu
-// showed them waiting on their own instruction / memory latency (long scoreboard 48 %, tensor pipe 6-9 %, issue slots
-// 20-33 % busy; profiles/r01_ncu_sdf_backward_summary.txt).  Half-width arrays fit 128 registers, so a CTA runs
-// 16 warps, every thread has its saved rows loaded and all four accumulator chunks fetched before it starts computing, and
-// the per-tile dependent chain between two MMA groups is half as long.  The few per-point scalars that need both halves
-// (sdf = w_n . a_n, d sdf/dx, dL/dx) cross through a 2 KB shared-memory hand-over, ordered by the tile's named barrier.
+// showed them waiting on their own loads (long scoreboard 48 %, tensor pipe 6-9 %, issue slots 20-33 % busy;
+// profiles/r01_ncu_sdf_backward_summary.txt).  With half-width arrays a CTA runs 16 warps at 128 registers and the per-tile
+// dependent chain between two MMA groups is half as long.  What matters at 128 registers is that NO loaded value is spilled
+// (a spill store waits for its load, which serialises the prefetch): the epilogues therefore work in 8-column chunks, the saved
+// rows of a layer are prefetched under its MMAs (kernel T: two chunks ahead of their use), and wide per-point arrays (the 96
+// d feat/dx rows) are consumed level by level.  The few per-point scalars that need both halves (sdf = w_n . a_n, d sdf/dx,
+// dL/dx) cross through a 2 KB shared-memory hand-over, ordered by the tile's named barrier.  Measured steps: DESIGN.md 4.
+//
+// Batched second point set: the points behind the first Pf (eikonal samples riding behind the main-pass points) skip the
+// feature head (kernel A) and have no upstream sdf / feature gradient (kernel R); everything else treats them like any point.
 #include "sdf_tc_plan.cuh"
 #include "tc_tile2.cuh"
 
